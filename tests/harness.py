@@ -1,0 +1,264 @@
+"""Multi-replica test harness: runs `world` replicas as processes (the product shape: one process per
+replica) or as threads of one process, on one GPU (all replicas share cuda:0 — what the round-end
+`pytest -m gpu` box offers) or on one GPU per replica.
+
+Every replica regenerates the seeded inputs of ALL replicas on the CPU, pushes its own to the GPU,
+calls the CUDA path through the C ABI (torch_on_k8s_b200.comm.Communicator -> libtok8s) and compares
+the result bit-for-bit with oracle/allreduce_oracle.py.
+"""
+from __future__ import annotations
+
+import multiprocessing as mp
+import os
+import sys
+import tempfile
+import threading
+import time
+import traceback
+from typing import Dict, List, Optional
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+NP2TOK = {"f32": 0, "bf16": 1, "f16": 2}
+
+
+def torch_dtype(name):
+    import torch
+    return {"f32": torch.float32, "bf16": torch.bfloat16, "f16": torch.float16}[name]
+
+
+def gen_input(seed: int, rank: int, count: int, dtype: str, pattern: str = "randn") -> np.ndarray:
+    """Seeded synthetic bucket of replica `rank` in storage form (see oracle dtype vocabulary)."""
+    from oracle.allreduce_oracle import from_f32
+    rs = np.random.RandomState((seed * 1000003 + rank * 7919 + 17) % (2 ** 31 - 1))
+    if pattern == "randn":
+        x = rs.standard_normal(count).astype(np.float32)
+    elif pattern == "ints":  # exactly representable: sums are order independent
+        x = (rs.randint(-8, 9, size=count)).astype(np.float32) * np.float32(0.25)
+    elif pattern == "rank":  # rank+1 everywhere (nccl-tests style)
+        x = np.full(count, float(rank + 1), dtype=np.float32)
+    elif pattern == "wide":  # wide dynamic range: exposes accumulation-order differences
+        x = (rs.standard_normal(count) * np.exp(rs.uniform(-12, 12, size=count))).astype(np.float32)
+    else:
+        raise ValueError(pattern)
+    return from_f32(x, dtype)
+
+
+def to_torch(a: np.ndarray, dtype: str, device):
+    import torch
+    if dtype == "bf16":
+        t = torch.from_numpy(a.view(np.int16).copy()).view(torch.bfloat16)
+    elif dtype == "f16":
+        t = torch.from_numpy(a.copy())
+    else:
+        t = torch.from_numpy(a.copy())
+    return t.to(device)
+
+
+def from_torch(t, dtype: str) -> np.ndarray:
+    import torch
+    t = t.detach().cpu().contiguous()
+    if dtype == "bf16":
+        return t.view(torch.int16).numpy().view(np.uint16)
+    return t.numpy()
+
+
+def bits_equal(a: np.ndarray, b: np.ndarray, dtype: str) -> bool:
+    if dtype == "f32":
+        return np.array_equal(np.asarray(a, np.float32).view(np.uint32),
+                              np.asarray(b, np.float32).view(np.uint32))
+    if dtype == "f16":
+        return np.array_equal(np.asarray(a, np.float16).view(np.uint16),
+                              np.asarray(b, np.float16).view(np.uint16))
+    return np.array_equal(np.asarray(a, np.uint16), np.asarray(b, np.uint16))
+
+
+def run_cases(rank: int, world: int, device: int, path: str, cases: List[dict],
+              job: str = "harness") -> List[dict]:
+    """Body of one replica.  Returns one result dict per case."""
+    import torch
+    from oracle.allreduce_oracle import allreduce_f32_unrounded, allreduce_oracle, to_f32, ulp_distance
+    from torch_on_k8s_b200.comm import Communicator
+
+    torch.cuda.set_device(device)
+    dev = torch.device("cuda", device)
+    comm = Communicator(job, rank, world, device, rendezvous_path=path)
+    stream = torch.cuda.Stream(device=dev)
+    results = []
+    caps = comm.caps()
+    try:
+        for ci, case in enumerate(cases):
+            count = case["count"]
+            din, dw, dout = case["in"], case["wire"], case["out"]
+            scale = case.get("scale", 1.0 / world)
+            post = case.get("post", False)
+            algo = case.get("algo", 0)
+            pattern = case.get("pattern", "randn")
+            seed = case.get("seed", 1234 + ci)
+            inplace = case.get("inplace", din == dout)
+            if algo == 4 and not caps.multicast:
+                results.append(dict(case=case, skipped="no multicast"))
+                continue
+            if algo == 1 and world != 1:
+                continue
+            inputs = [gen_input(seed, r, count, din, pattern) for r in range(world)]
+            want = allreduce_oracle(inputs, din, dw, dout, scale, post)
+            with torch.cuda.stream(stream):
+                x = to_torch(inputs[rank], din, dev)
+                y = x if inplace else torch.empty(count, dtype=torch_dtype(dout), device=dev)
+                t0 = time.perf_counter()
+                comm.allreduce_bucket(x, y, scale=scale, wire_dtype=torch_dtype(dw),
+                                      post_scale=post, algo=algo, stream=stream)
+                stream.synchronize()
+                ms = (time.perf_counter() - t0) * 1e3
+            comm.status()
+            got = from_torch(y, dout)
+            exact = bits_equal(got, want, dout)
+            res = dict(case=case, exact=bool(exact), ms=ms, rank=rank)
+            if not exact:
+                ulp = ulp_distance(got, want, dout)
+                res["max_ulp"] = int(ulp.max())
+                res["mismatch"] = int((ulp != 0).sum())
+                ref = allreduce_f32_unrounded(inputs, din, dw, scale, post)
+                err = np.abs(to_f32(got, dout).astype(np.float64) - ref)
+                denom = max(float(np.abs(ref).max()), 1e-30)
+                res["normwise"] = float(err.max() / denom)
+                bad = np.nonzero(ulp)[0][:4]
+                res["first_bad"] = [int(i) for i in bad]
+            results.append(res)
+        res_launch = comm.launches()
+        results.append(dict(launches=res_launch, multicast=int(caps.multicast), rank=rank))
+    finally:
+        comm.close()
+    return results
+
+
+def _proc_entry(rank, world, device, path, cases, job, env, q):
+    try:
+        os.environ.update(env or {})
+        q.put((rank, "ok", run_cases(rank, world, device, path, cases, job)))
+    except Exception:  # noqa: BLE001
+        q.put((rank, "error", traceback.format_exc()))
+
+
+def launch(world: int, cases: List[dict], *, devices: Optional[List[int]] = None,
+           mode: str = "proc", timeout: float = 300.0, env: Optional[Dict[str, str]] = None,
+           job: str = "harness") -> Dict[int, list]:
+    """Run `cases` on `world` replicas; returns {rank: results}.  Raises on replica failure."""
+    devices = devices or [0] * world
+    tmp = tempfile.mkdtemp(prefix="tok8s-")
+    path = os.path.join(tmp, "rdzv")
+    out: Dict[int, list] = {}
+    if mode == "proc":
+        ctx = mp.get_context("spawn")
+        q = ctx.Queue()
+        procs = [ctx.Process(target=_proc_entry,
+                             args=(r, world, devices[r], path, cases, job, env, q), daemon=True)
+                 for r in range(world)]
+        for p in procs:
+            p.start()
+        deadline = time.time() + timeout
+        errors = []
+        try:
+            while len(out) + len(errors) < world:
+                left = deadline - time.time()
+                if left <= 0:
+                    raise TimeoutError("replicas did not finish within %.0f s" % timeout)
+                try:
+                    rank, status, payload = q.get(timeout=min(left, 5.0))
+                except Exception:  # queue.Empty
+                    if any(p.exitcode not in (None, 0) for p in procs):
+                        dead = [i for i, p in enumerate(procs) if p.exitcode not in (None, 0)]
+                        raise RuntimeError("replica(s) %s died (exit codes %s)" %
+                                           (dead, [procs[i].exitcode for i in dead]))
+                    continue
+                if status == "ok":
+                    out[rank] = payload
+                else:
+                    errors.append((rank, payload))
+        finally:
+            for p in procs:
+                p.join(timeout=10)
+                if p.is_alive():
+                    p.kill()
+        if errors:
+            raise RuntimeError("replica %d failed:\n%s" % errors[0])
+    elif mode == "thread":
+        if env:
+            os.environ.update(env)
+        errs = []
+
+        def body(r):
+            try:
+                out[r] = run_cases(r, world, devices[r], path, cases, job)
+            except Exception:  # noqa: BLE001
+                errs.append((r, traceback.format_exc()))
+
+        ts = [threading.Thread(target=body, args=(r,), daemon=True) for r in range(world)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join(timeout)
+        if any(t.is_alive() for t in ts):
+            raise TimeoutError("replica threads did not finish within %.0f s" % timeout)
+        if errs:
+            raise RuntimeError("replica %d failed:\n%s" % errs[0])
+    else:
+        raise ValueError(mode)
+    return out
+
+
+def summarize(results: Dict[int, list]) -> dict:
+    total = bad = skipped = 0
+    worst = []
+    for rank, rs in results.items():
+        for r in rs:
+            if "case" not in r:
+                continue
+            if "skipped" in r:
+                skipped += 1
+                continue
+            total += 1
+            if not r["exact"]:
+                bad += 1
+                worst.append(r)
+    return dict(total=total, bad=bad, skipped=skipped, worst=worst[:8])
+
+
+TRIPLES_CORE = [("f32", "f32", "f32"), ("bf16", "bf16", "bf16"), ("f16", "f16", "f16"),
+                ("f32", "bf16", "f32")]
+TRIPLES_MIXED = [("bf16", "f32", "bf16"), ("f32", "bf16", "bf16"), ("f32", "f16", "f32"),
+                 ("bf16", "bf16", "f32"), ("f16", "f32", "f32")]
+
+
+def standard_cases(world: int, algos, quick: bool = False) -> List[dict]:
+    """The parity matrix: dtype triples x ragged/edge sizes x PRE/POST scale x algorithms."""
+    counts = [1, 7, 8, 9, 1000, 4097, 65536 + 3, (1 << 20) + 5]
+    if quick:
+        counts = [1, 9, 4097, 65536 + 3]
+    cases = []
+    seed = 100
+    for algo in algos:
+        for (a, w, o) in TRIPLES_CORE:
+            for n in counts:
+                seed += 1
+                cases.append(dict(count=n, **{"in": a, "wire": w, "out": o}, algo=algo, seed=seed,
+                                  scale=1.0 / world))
+        for (a, w, o) in TRIPLES_MIXED:
+            for n in (9, 4097, 65536 + 3):
+                seed += 1
+                cases.append(dict(count=n, **{"in": a, "wire": w, "out": o}, algo=algo, seed=seed,
+                                  scale=1.0 / world))
+        # POST scale with a non power-of-two factor, wide dynamic range, out-of-place
+        for (a, w, o) in TRIPLES_CORE:
+            seed += 1
+            cases.append(dict(count=30011, **{"in": a, "wire": w, "out": o}, algo=algo, seed=seed,
+                              scale=1.0 / 3.0, post=True, pattern="wide", inplace=False))
+            seed += 1
+            cases.append(dict(count=30011, **{"in": a, "wire": w, "out": o}, algo=algo, seed=seed,
+                              scale=1.0 / 3.0, post=False, pattern="wide", inplace=False))
+    return cases

@@ -1,0 +1,757 @@
+// allreduce.cu — the data-parallel hot path: per-step DDP gradient-bucket allreduce across the
+// job's replicas, fused with the bucket cast/scale, hand-written for sm_100a.
+//
+// Replaces (reference side, third-party): DDP default comm hook `tensor.div_(N)` + `all_reduce`
+// (torch/distributed/algorithms/ddp_comm_hooks/default_hooks.py:18-33), the compress hooks' cast +
+// scale (:57-92) and ProcessGroupGloo/NCCL::allreduce, which the reference operator only configures
+// (controllers/train/torchjob_controller.go:394-446).
+//
+// Semantics (all algorithms, every replica bit-identical):
+//     wire_r[i] = cast_wire( f32(in_r[i]) * pre )                pre  = scale (PRE) or 1 (POST)
+//     acc[i]    = f32(wire_0[i]) + f32(wire_1[i]) + ... (rank order, fp32)
+//     out[i]    = cast_out( f32( cast_wire( acc[i] * post ) ) )  post = 1 (PRE) or scale (POST)
+// (NVLS: the switch performs the fp32-accumulated sum; its order is unspecified.)
+//
+// Kernels (one launch per bucket, 512 threads/CTA, CTA b of every replica owns the same slab of
+// 16-byte packs so that all cross-replica dependencies are between same-index CTAs and a per-CTA
+// flag barrier in peer HBM is sufficient — no grid-wide sync):
+//   local     (world 1)  out = cast(in*scale): HBM-bound copy, grid = k x SMs
+//   one-shot  push wire packs into slot[rank] of every peer's staging buffer; barrier; reduce the
+//             `world` local slots                                              1 barrier, (N-1)S out
+//   two-shot  stage locally; barrier; replica r reduces sub-slab r from all peers (LDG.128 over
+//             NVLink, all peers in flight), writes it back in place; barrier; pull the other
+//             sub-slabs                                                  2 barriers, 2(N-1)/N S
+//   nvls      stage locally; barrier; multimem.ld_reduce sub-slab r through the NVSwitch multicast
+//             mapping and multimem.st the result to every replica; barrier; local copy-out
+// Tensor cores are deliberately unused: this is a bandwidth-bound reduction, not a contraction.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <type_traits>
+
+#include "tok_internal.h"
+
+namespace tok {
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// PTX helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// Data written by other GPUs during this kernel is always read at system scope (served by the
+// home L2, never by a stale local L1 line).
+__device__ __forceinline__ uint4 ld_sys(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ uint2 ld_sys(const uint2* p) {
+  uint2 v;
+  asm volatile("ld.relaxed.sys.global.v2.u32 {%0,%1}, [%2];"
+               : "=r"(v.x), "=r"(v.y)
+               : "l"(p)
+               : "memory");
+  return v;
+}
+
+template <int BYTES>
+struct RawT;
+template <>
+struct RawT<16> {
+  using type = uint4;
+};
+template <>
+struct RawT<8> {
+  using type = uint2;
+};
+
+// ------------------------------------------------------------------------------------------------
+// pack <-> fp32 conversion.  A pack is P elements; P = 4 when any dtype of the launch is f32
+// (16 B of f32, 8 B of a 16-bit type), else 8 (16 B of a 16-bit type).
+// ------------------------------------------------------------------------------------------------
+template <class T, int P>
+struct Cvt;
+
+template <>
+struct Cvt<float, 4> {
+  using raw_t = uint4;
+  static __device__ __forceinline__ void to_f32(const raw_t& r, float (&v)[4]) {
+    v[0] = __uint_as_float(r.x);
+    v[1] = __uint_as_float(r.y);
+    v[2] = __uint_as_float(r.z);
+    v[3] = __uint_as_float(r.w);
+  }
+  static __device__ __forceinline__ raw_t from_f32(const float (&v)[4]) {
+    return make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]),
+                      __float_as_uint(v[3]));
+  }
+  static __device__ __forceinline__ float scalar(float x) { return x; }
+  static __device__ __forceinline__ float from_scalar(float x) { return x; }
+};
+
+template <int P>
+struct Cvt<__nv_bfloat16, P> {
+  using raw_t = typename RawT<2 * P>::type;
+  static __device__ __forceinline__ void to_f32(const raw_t& r, float (&v)[P]) {
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(&r);
+#pragma unroll
+    for (int k = 0; k < P / 2; ++k) {
+      v[2 * k] = __uint_as_float(w[k] << 16);
+      v[2 * k + 1] = __uint_as_float(w[k] & 0xffff0000u);
+    }
+  }
+  static __device__ __forceinline__ raw_t from_f32(const float (&v)[P]) {
+    raw_t r;
+    uint32_t* w = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+    for (int k = 0; k < P / 2; ++k) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
+      w[k] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    return r;
+  }
+  static __device__ __forceinline__ float scalar(__nv_bfloat16 x) { return __bfloat162float(x); }
+  static __device__ __forceinline__ __nv_bfloat16 from_scalar(float x) {
+    return __float2bfloat16_rn(x);
+  }
+};
+
+template <int P>
+struct Cvt<__half, P> {
+  using raw_t = typename RawT<2 * P>::type;
+  static __device__ __forceinline__ void to_f32(const raw_t& r, float (&v)[P]) {
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(&r);
+#pragma unroll
+    for (int k = 0; k < P / 2; ++k) {
+      float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[k]));
+      v[2 * k] = f.x;
+      v[2 * k + 1] = f.y;
+    }
+  }
+  static __device__ __forceinline__ raw_t from_f32(const float (&v)[P]) {
+    raw_t r;
+    uint32_t* w = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+    for (int k = 0; k < P / 2; ++k) {
+      __half2 h = __floats2half2_rn(v[2 * k], v[2 * k + 1]);
+      w[k] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    return r;
+  }
+  static __device__ __forceinline__ float scalar(__half x) { return __half2float(x); }
+  static __device__ __forceinline__ __half from_scalar(float x) { return __float2half_rn(x); }
+};
+
+// ------------------------------------------------------------------------------------------------
+// NVSwitch multicast (NVLS) load-reduce / store, fp32 accumulation inside the switch.
+// ------------------------------------------------------------------------------------------------
+template <class T, int BYTES>
+struct MM;
+template <>
+struct MM<float, 16> {
+  static __device__ __forceinline__ uint4 ld_reduce(const void* p) {
+    uint4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(*reinterpret_cast<float*>(&v.x)), "=f"(*reinterpret_cast<float*>(&v.y)),
+                   "=f"(*reinterpret_cast<float*>(&v.z)), "=f"(*reinterpret_cast<float*>(&v.w))
+                 : "l"(p)
+                 : "memory");
+    return v;
+  }
+  static __device__ __forceinline__ void st(void* p, const uint4& v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p),
+                 "f"(__uint_as_float(v.x)), "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)),
+                 "f"(__uint_as_float(v.w))
+                 : "memory");
+  }
+};
+#define TOK_MM_16BIT(T, SFX)                                                                      \
+  template <>                                                                                     \
+  struct MM<T, 16> {                                                                              \
+    static __device__ __forceinline__ uint4 ld_reduce(const void* p) {                            \
+      uint4 v;                                                                                    \
+      asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4." SFX                   \
+                   " {%0,%1,%2,%3}, [%4];"                                                        \
+                   : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)                                   \
+                   : "l"(p)                                                                       \
+                   : "memory");                                                                   \
+      return v;                                                                                   \
+    }                                                                                             \
+    static __device__ __forceinline__ void st(void* p, const uint4& v) {                          \
+      asm volatile("multimem.st.relaxed.sys.global.v4." SFX " [%0], {%1,%2,%3,%4};" ::"l"(p),     \
+                   "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)                                         \
+                   : "memory");                                                                   \
+    }                                                                                             \
+  };                                                                                              \
+  template <>                                                                                     \
+  struct MM<T, 8> {                                                                               \
+    static __device__ __forceinline__ uint2 ld_reduce(const void* p) {                            \
+      uint2 v;                                                                                    \
+      asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v2." SFX                   \
+                   " {%0,%1}, [%2];"                                                              \
+                   : "=r"(v.x), "=r"(v.y)                                                         \
+                   : "l"(p)                                                                       \
+                   : "memory");                                                                   \
+      return v;                                                                                   \
+    }                                                                                             \
+    static __device__ __forceinline__ void st(void* p, const uint2& v) {                          \
+      asm volatile("multimem.st.relaxed.sys.global.v2." SFX " [%0], {%1,%2};" ::"l"(p), "r"(v.x), \
+                   "r"(v.y)                                                                       \
+                   : "memory");                                                                   \
+    }                                                                                             \
+  };
+TOK_MM_16BIT(__nv_bfloat16, "bf16x2")
+TOK_MM_16BIT(__half, "f16x2")
+#undef TOK_MM_16BIT
+
+// ------------------------------------------------------------------------------------------------
+// Per-CTA cross-replica barrier.  CTA b of rank r publishes `target` into flag[b][r] of every
+// replica (release, system scope) and waits until flag[b][p] of its own heap reached `target` for
+// every p (acquire).  Values only grow; a replica can be at most one barrier ahead, so one flag word
+// per (CTA, source) suffices.  Gives up on host abort or after timeout_ns (a dead peer must not
+// hang the GPU).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool cta_barrier(const KArgs& a, uint32_t target, int* s_fail) {
+  __syncthreads();
+  const int t = threadIdx.x;
+  if (t < a.world) {
+    uint32_t* remote =
+        reinterpret_cast<uint32_t*>(a.peer[t]) + (blockIdx.x * kMaxWorld + a.rank);
+    st_release_sys(remote, target);
+    const uint32_t* mine =
+        reinterpret_cast<const uint32_t*>(a.peer[a.rank]) + (blockIdx.x * kMaxWorld + t);
+    unsigned long long t0 = 0;
+    uint32_t spins = 0;
+    while (static_cast<int32_t>(ld_acquire_sys(mine) - target) < 0) {
+      if ((++spins & 0xffu) == 0) {
+        if (a.hostctl[kCtlAbort] != 0) {
+          a.hostctl[kCtlStatus] = 2;
+          *s_fail = 1;
+          break;
+        }
+        const unsigned long long now = globaltimer_ns();
+        if (t0 == 0) {
+          t0 = now;
+        } else if (now - t0 > a.timeout_ns) {
+          a.hostctl[kCtlStatus] = 1;
+          *s_fail = 1;
+          break;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  return *s_fail == 0;
+}
+
+struct CtaState {
+  uint32_t seq;   // launches completed before this one (buffer parity)
+  uint32_t bar;   // barriers this CTA index has passed
+};
+
+__device__ __forceinline__ CtaState cta_begin(const KArgs& a, uint32_t* s_words, int* s_fail) {
+  if (threadIdx.x == 0) {
+    s_words[0] = a.ctr[kCtrCallSeq];
+    s_words[1] = a.ctr[blockIdx.x];
+    *s_fail = 0;
+  }
+  __syncthreads();
+  CtaState st;
+  st.seq = s_words[0];
+  st.bar = s_words[1];
+  return st;
+}
+
+// Last CTA out bumps the launch sequence (selects the other staging buffer next time); works under
+// CUDA-graph replay because nothing about the sequence lives on the host.
+__device__ __forceinline__ void cta_end(const KArgs& a, const CtaState& st) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    a.ctr[blockIdx.x] = st.bar;
+    __threadfence();
+    const unsigned ticket = atomicAdd(&a.ctr[kCtrDone], 1u);
+    if (ticket == gridDim.x - 1) {
+      a.ctr[kCtrDone] = 0;
+      a.ctr[kCtrCallSeq] = st.seq + 1;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// The kernels.
+// ------------------------------------------------------------------------------------------------
+template <class IN, class WIRE, class OUT>
+struct AR {
+  static constexpr int kMaxSz =
+      sizeof(IN) > sizeof(WIRE) ? (sizeof(IN) > sizeof(OUT) ? sizeof(IN) : sizeof(OUT))
+                                : (sizeof(WIRE) > sizeof(OUT) ? sizeof(WIRE) : sizeof(OUT));
+  static constexpr int P = 16 / kMaxSz;
+  using CI = Cvt<IN, P>;
+  using CW = Cvt<WIRE, P>;
+  using CO = Cvt<OUT, P>;
+  using RI = typename CI::raw_t;
+  using RW = typename CW::raw_t;
+  using RO = typename CO::raw_t;
+
+  // in pack -> wire pack (fused cast + pre-scale)
+  static __device__ __forceinline__ RW in_to_wire(const RI& r, float pre) {
+    float v[P];
+    CI::to_f32(r, v);
+#pragma unroll
+    for (int k = 0; k < P; ++k) v[k] *= pre;
+    return CW::from_f32(v);
+  }
+  // partial last pack of `in` (count % P != 0), zero padded
+  static __device__ __forceinline__ RW in_tail_to_wire(const KArgs& a, size_t pack, float pre) {
+    const IN* in = static_cast<const IN*>(a.in);
+    float v[P];
+#pragma unroll
+    for (int k = 0; k < P; ++k) {
+      const size_t e = pack * P + k;
+      v[k] = e < a.count ? CI::scalar(in[e]) * pre : 0.f;
+    }
+    return CW::from_f32(v);
+  }
+  // wire pack -> out (vector store, or guarded scalar stores for the partial last pack)
+  static __device__ __forceinline__ void wire_to_out(const KArgs& a, size_t pack, const RW& w) {
+    OUT* out = static_cast<OUT*>(a.out);
+    const size_t full = a.count / P;
+    if (pack < full) {
+      if constexpr (std::is_same<WIRE, OUT>::value) {
+        reinterpret_cast<RW*>(out)[pack] = w;
+      } else {
+        float v[P];
+        CW::to_f32(w, v);
+        reinterpret_cast<RO*>(out)[pack] = CO::from_f32(v);
+      }
+    } else {
+      float v[P];
+      CW::to_f32(w, v);
+#pragma unroll
+      for (int k = 0; k < P; ++k) {
+        const size_t e = pack * P + k;
+        if (e < a.count) out[e] = CO::from_scalar(v[k]);
+      }
+    }
+  }
+
+  // ---- phase 0 (two-shot / NVLS): in -> own staging buffer, packs [lo, hi) -----------------------
+  static __device__ __forceinline__ void stage_local(const KArgs& a, RW* dst, size_t lo, size_t hi,
+                                                     float pre) {
+    const RI* in = static_cast<const RI*>(a.in);
+    const size_t full = a.count / P;
+    const size_t hv = hi < full ? hi : full;
+    constexpr int U = 4;
+    size_t i = lo + threadIdx.x;
+    for (; i + (U - 1) * kThreads < hv; i += U * kThreads) {
+      RI r[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) r[u] = __ldcs(in + i + u * kThreads);
+#pragma unroll
+      for (int u = 0; u < U; ++u) dst[i + u * kThreads] = in_to_wire(r[u], pre);
+    }
+    for (; i < hv; i += kThreads) dst[i] = in_to_wire(__ldcs(in + i), pre);
+    if (threadIdx.x == 0 && full < a.total_packs && full >= lo && full < hi)
+      dst[full] = in_tail_to_wire(a, full, pre);
+  }
+
+  // ---- phase 0 (one-shot): in -> slot[rank] of every replica's staging buffer ---------------------
+  static __device__ __forceinline__ void stage_push(const KArgs& a, int q, size_t lo, size_t hi,
+                                                    float pre) {
+    const RI* in = static_cast<const RI*>(a.in);
+    RW* dst[kMaxWorld];
+#pragma unroll
+    for (int p = 0; p < kMaxWorld; ++p)
+      dst[p] = reinterpret_cast<RW*>(a.peer[p < a.world ? p : 0] + a.stage_off[q] +
+                                     static_cast<size_t>(a.rank) * a.slot_bytes);
+    const size_t full = a.count / P;
+    const size_t hv = hi < full ? hi : full;
+    constexpr int U = 2;
+    size_t i = lo + threadIdx.x;
+    for (; i + (U - 1) * kThreads < hv; i += U * kThreads) {
+      RI r[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) r[u] = __ldcs(in + i + u * kThreads);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const RW w = in_to_wire(r[u], pre);
+#pragma unroll
+        for (int p = 0; p < kMaxWorld; ++p)
+          if (p < a.world) dst[p][i + u * kThreads] = w;
+      }
+    }
+    for (; i < hv; i += kThreads) {
+      const RW w = in_to_wire(__ldcs(in + i), pre);
+#pragma unroll
+      for (int p = 0; p < kMaxWorld; ++p)
+        if (p < a.world) dst[p][i] = w;
+    }
+    if (threadIdx.x == 0 && full < a.total_packs && full >= lo && full < hi) {
+      const RW w = in_tail_to_wire(a, full, pre);
+#pragma unroll
+      for (int p = 0; p < kMaxWorld; ++p)
+        if (p < a.world) dst[p][full] = w;
+    }
+  }
+
+  // ---- rank-ordered fp32 reduction of packs [lo, hi) from src[0..world) --------------------------
+  // Every load of a batch is issued before the first add: world x U 16-byte requests in flight per
+  // thread hide the ~2 us NVLink round trip.  `mine` (two-shot) receives the reduced wire pack in
+  // place so that peers can pull it in phase 2.
+  template <int MAXW, int U>
+  static __device__ __forceinline__ void reduce_packs(const KArgs& a, const RW* const (&src)[kMaxWorld],
+                                                      RW* mine, size_t lo, size_t hi, float post) {
+    size_t i = lo + threadIdx.x;
+    for (; i + (U - 1) * kThreads < hi; i += U * kThreads) {
+      RW r[U][MAXW];
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int p = 0; p < MAXW; ++p)
+          if (p < a.world) r[u][p] = ld_sys(src[p] + i + u * kThreads);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        float acc[P];
+        CW::to_f32(r[u][0], acc);
+#pragma unroll
+        for (int p = 1; p < MAXW; ++p)
+          if (p < a.world) {
+            float v[P];
+            CW::to_f32(r[u][p], v);
+#pragma unroll
+            for (int k = 0; k < P; ++k) acc[k] += v[k];
+          }
+#pragma unroll
+        for (int k = 0; k < P; ++k) acc[k] *= post;
+        const RW w = CW::from_f32(acc);
+        if (mine) mine[i + u * kThreads] = w;
+        wire_to_out(a, i + u * kThreads, w);
+      }
+    }
+    for (; i < hi; i += kThreads) {
+      RW r[MAXW];
+#pragma unroll
+      for (int p = 0; p < MAXW; ++p)
+        if (p < a.world) r[p] = ld_sys(src[p] + i);
+      float acc[P];
+      CW::to_f32(r[0], acc);
+#pragma unroll
+      for (int p = 1; p < MAXW; ++p)
+        if (p < a.world) {
+          float v[P];
+          CW::to_f32(r[p], v);
+#pragma unroll
+          for (int k = 0; k < P; ++k) acc[k] += v[k];
+        }
+#pragma unroll
+      for (int k = 0; k < P; ++k) acc[k] *= post;
+      const RW w = CW::from_f32(acc);
+      if (mine) mine[i] = w;
+      wire_to_out(a, i, w);
+    }
+  }
+
+  static __device__ __forceinline__ void reduce_dispatch(const KArgs& a,
+                                                         const RW* const (&src)[kMaxWorld], RW* mine,
+                                                         size_t lo, size_t hi, float post) {
+    if (a.world <= 4)
+      reduce_packs<4, 4>(a, src, mine, lo, hi, post);
+    else
+      reduce_packs<kMaxWorld, 2>(a, src, mine, lo, hi, post);
+  }
+
+  // ---- phase 2 (two-shot): pull the other replicas' reduced sub-slabs -----------------------------
+  // (peer, offset) is flattened so that every thread keeps 8 independent remote loads in flight
+  // whatever the world size.
+  static __device__ __forceinline__ void gather_packs(const KArgs& a, int q, size_t slab_lo,
+                                                      size_t M) {
+    const size_t J = static_cast<size_t>(a.world - 1) * M;
+    constexpr int U = 8;
+    auto locate = [&](size_t j, const RW*& p_src, size_t& idx) -> bool {
+      int pp = 0;
+#pragma unroll
+      for (int k = 1; k < kMaxWorld - 1; ++k) pp += (j >= k * M) ? 1 : 0;
+      const size_t off = j - pp * M;
+      int p = a.rank + 1 + pp;
+      if (p >= a.world) p -= a.world;
+      idx = slab_lo + static_cast<size_t>(p) * M + off;
+      p_src = reinterpret_cast<const RW*>(a.peer[p] + a.stage_off[q]);
+      return idx < a.total_packs;
+    };
+    size_t j = threadIdx.x;
+    for (; j + (U - 1) * kThreads < J; j += U * kThreads) {
+      RW r[U];
+      size_t idx[U];
+      bool ok[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const RW* s;
+        ok[u] = locate(j + u * kThreads, s, idx[u]);
+        if (ok[u]) r[u] = ld_sys(s + idx[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (ok[u]) wire_to_out(a, idx[u], r[u]);
+    }
+    for (; j < J; j += kThreads) {
+      const RW* s;
+      size_t idx;
+      if (locate(j, s, idx)) wire_to_out(a, idx, ld_sys(s + idx));
+    }
+  }
+
+  // ---- phase 2 (NVLS): local staging -> out over packs [lo, hi) -----------------------------------
+  static __device__ __forceinline__ void copy_out(const KArgs& a, const RW* src, size_t lo,
+                                                  size_t hi) {
+    constexpr int U = 8;
+    size_t i = lo + threadIdx.x;
+    for (; i + (U - 1) * kThreads < hi; i += U * kThreads) {
+      RW r[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) r[u] = ld_sys(src + i + u * kThreads);
+#pragma unroll
+      for (int u = 0; u < U; ++u) wire_to_out(a, i + u * kThreads, r[u]);
+    }
+    for (; i < hi; i += kThreads) wire_to_out(a, i, ld_sys(src + i));
+  }
+
+  // ---- NVLS phase 1: in-switch reduce of my sub-slab, broadcast of the result ----------------------
+  static __device__ __forceinline__ void nvls_reduce(const KArgs& a, char* mc_stage, size_t lo,
+                                                     size_t hi, float post) {
+    using M = MM<WIRE, sizeof(RW)>;
+    RW* mc = reinterpret_cast<RW*>(mc_stage);
+    constexpr int U = 4;
+    auto finish = [&](size_t idx, RW r) {
+      if (post != 1.f) {
+        float v[P];
+        CW::to_f32(r, v);
+#pragma unroll
+        for (int k = 0; k < P; ++k) v[k] *= post;
+        r = CW::from_f32(v);
+      }
+      M::st(mc + idx, r);
+    };
+    size_t i = lo + threadIdx.x;
+    for (; i + (U - 1) * kThreads < hi; i += U * kThreads) {
+      RW r[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) r[u] = M::ld_reduce(mc + i + u * kThreads);
+#pragma unroll
+      for (int u = 0; u < U; ++u) finish(i + u * kThreads, r[u]);
+    }
+    for (; i < hi; i += kThreads) finish(i, M::ld_reduce(mc + i));
+  }
+};
+
+template <class T>
+__device__ __forceinline__ T min_sz(T a, T b) {
+  return a < b ? a : b;
+}
+
+// world == 1: fused scale/cast only.
+template <class IN, class WIRE, class OUT>
+__global__ void __launch_bounds__(kThreads) local_kernel(const __grid_constant__ KArgs a) {
+  using A = AR<IN, WIRE, OUT>;
+  const float pre = (a.flags & TOK_FLAG_SCALE_POST) ? 1.f : a.scale;
+  const float post = (a.flags & TOK_FLAG_SCALE_POST) ? a.scale : 1.f;
+  const typename A::RI* in = static_cast<const typename A::RI*>(a.in);
+  const size_t full = a.count / A::P;
+  constexpr int U = 4;
+  const size_t stride = static_cast<size_t>(gridDim.x) * kThreads;
+  auto finish = [&](size_t idx, typename A::RW w) {
+    if (post != 1.f) {
+      float v[A::P];
+      A::CW::to_f32(w, v);
+#pragma unroll
+      for (int k = 0; k < A::P; ++k) v[k] *= post;
+      w = A::CW::from_f32(v);
+    }
+    A::wire_to_out(a, idx, w);
+  };
+  size_t i = static_cast<size_t>(blockIdx.x) * kThreads + threadIdx.x;
+  for (; i + (U - 1) * stride < full; i += U * stride) {
+    typename A::RI r[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) r[u] = __ldcs(in + i + u * stride);
+#pragma unroll
+    for (int u = 0; u < U; ++u) finish(i + u * stride, A::in_to_wire(r[u], pre));
+  }
+  for (; i < full; i += stride) finish(i, A::in_to_wire(__ldcs(in + i), pre));
+  if (blockIdx.x == 0 && threadIdx.x == 0 && full < a.total_packs)
+    finish(full, A::in_tail_to_wire(a, full, pre));
+}
+
+template <class IN, class WIRE, class OUT>
+__global__ void __launch_bounds__(kThreads, 1) one_shot_kernel(const __grid_constant__ KArgs a) {
+  using A = AR<IN, WIRE, OUT>;
+  __shared__ uint32_t s_words[2];
+  __shared__ int s_fail;
+  CtaState st = cta_begin(a, s_words, &s_fail);
+  const int q = st.seq & 1;
+  const float pre = (a.flags & TOK_FLAG_SCALE_POST) ? 1.f : a.scale;
+  const float post = (a.flags & TOK_FLAG_SCALE_POST) ? a.scale : 1.f;
+  const size_t lo = static_cast<size_t>(blockIdx.x) * a.packs_per_cta;
+  const size_t hi = min_sz(lo + a.packs_per_cta, a.total_packs);
+
+  A::stage_push(a, q, lo, hi, pre);
+  st.bar += 1;
+  if (cta_barrier(a, st.bar, &s_fail)) {
+    const typename A::RW* src[kMaxWorld];
+#pragma unroll
+    for (int p = 0; p < kMaxWorld; ++p)
+      src[p] = reinterpret_cast<const typename A::RW*>(a.peer[a.rank] + a.stage_off[q] +
+                                                       static_cast<size_t>(p) * a.slot_bytes);
+    A::reduce_dispatch(a, src, nullptr, lo, hi, post);
+  }
+  cta_end(a, st);
+}
+
+template <class IN, class WIRE, class OUT>
+__global__ void __launch_bounds__(kThreads, 1) two_shot_kernel(const __grid_constant__ KArgs a) {
+  using A = AR<IN, WIRE, OUT>;
+  __shared__ uint32_t s_words[2];
+  __shared__ int s_fail;
+  CtaState st = cta_begin(a, s_words, &s_fail);
+  const int q = st.seq & 1;
+  const float pre = (a.flags & TOK_FLAG_SCALE_POST) ? 1.f : a.scale;
+  const float post = (a.flags & TOK_FLAG_SCALE_POST) ? a.scale : 1.f;
+  const size_t lo = static_cast<size_t>(blockIdx.x) * a.packs_per_cta;
+  const size_t hi = min_sz(lo + a.packs_per_cta, a.total_packs);
+  const size_t M = a.packs_per_cta / a.world;  // sub-slab length
+  typename A::RW* mine = reinterpret_cast<typename A::RW*>(a.peer[a.rank] + a.stage_off[q]);
+
+  A::stage_local(a, mine, lo, hi, pre);
+  st.bar += 1;
+  bool ok = cta_barrier(a, st.bar, &s_fail);
+  if (ok) {
+    const typename A::RW* src[kMaxWorld];
+#pragma unroll
+    for (int p = 0; p < kMaxWorld; ++p)
+      src[p] = reinterpret_cast<const typename A::RW*>(a.peer[p < a.world ? p : 0] + a.stage_off[q]);
+    const size_t slo = min_sz(lo + static_cast<size_t>(a.rank) * M, hi);
+    const size_t shi = min_sz(slo + M, hi);
+    A::reduce_dispatch(a, src, mine, slo, shi, post);
+    st.bar += 1;
+    ok = cta_barrier(a, st.bar, &s_fail);
+  }
+  if (ok) A::gather_packs(a, q, lo, M);
+  cta_end(a, st);
+}
+
+template <class IN, class WIRE, class OUT>
+__global__ void __launch_bounds__(kThreads, 1) nvls_kernel(const __grid_constant__ KArgs a) {
+  using A = AR<IN, WIRE, OUT>;
+  __shared__ uint32_t s_words[2];
+  __shared__ int s_fail;
+  CtaState st = cta_begin(a, s_words, &s_fail);
+  const int q = st.seq & 1;
+  const float pre = (a.flags & TOK_FLAG_SCALE_POST) ? 1.f : a.scale;
+  const float post = (a.flags & TOK_FLAG_SCALE_POST) ? a.scale : 1.f;
+  const size_t lo = static_cast<size_t>(blockIdx.x) * a.packs_per_cta;
+  const size_t hi = min_sz(lo + a.packs_per_cta, a.total_packs);
+  const size_t M = a.packs_per_cta / a.world;
+  typename A::RW* mine = reinterpret_cast<typename A::RW*>(a.peer[a.rank] + a.stage_off[q]);
+
+  A::stage_local(a, mine, lo, hi, pre);
+  st.bar += 1;
+  bool ok = cta_barrier(a, st.bar, &s_fail);
+  if (ok) {
+    const size_t slo = min_sz(lo + static_cast<size_t>(a.rank) * M, hi);
+    const size_t shi = min_sz(slo + M, hi);
+    A::nvls_reduce(a, a.mc + a.stage_off[q], slo, shi, post);
+    st.bar += 1;
+    ok = cta_barrier(a, st.bar, &s_fail);
+  }
+  if (ok) A::copy_out(a, mine, lo, hi);
+  cta_end(a, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// dispatch
+// ------------------------------------------------------------------------------------------------
+template <class IN, class WIRE, class OUT>
+int launch_typed(int algo, int ctas, const KArgs& a, cudaStream_t s) {
+  switch (algo) {
+    case TOK_ALGO_LOCAL:
+      local_kernel<IN, WIRE, OUT><<<ctas, kThreads, 0, s>>>(a);
+      break;
+    case TOK_ALGO_ONE_SHOT:
+      one_shot_kernel<IN, WIRE, OUT><<<ctas, kThreads, 0, s>>>(a);
+      break;
+    case TOK_ALGO_TWO_SHOT:
+      two_shot_kernel<IN, WIRE, OUT><<<ctas, kThreads, 0, s>>>(a);
+      break;
+    case TOK_ALGO_NVLS:
+      nvls_kernel<IN, WIRE, OUT><<<ctas, kThreads, 0, s>>>(a);
+      break;
+    default:
+      return static_cast<int>(cudaErrorInvalidValue);
+  }
+  return static_cast<int>(cudaGetLastError());
+}
+
+template <class IN, class WIRE>
+int launch_out(int out_dtype, int algo, int ctas, const KArgs& a, cudaStream_t s) {
+  switch (out_dtype) {
+    case TOK_F32:
+      return launch_typed<IN, WIRE, float>(algo, ctas, a, s);
+    case TOK_BF16:
+      return launch_typed<IN, WIRE, __nv_bfloat16>(algo, ctas, a, s);
+    case TOK_F16:
+      return launch_typed<IN, WIRE, __half>(algo, ctas, a, s);
+  }
+  return static_cast<int>(cudaErrorInvalidValue);
+}
+
+template <class IN>
+int launch_wire(int wire_dtype, int out_dtype, int algo, int ctas, const KArgs& a, cudaStream_t s) {
+  switch (wire_dtype) {
+    case TOK_F32:
+      return launch_out<IN, float>(out_dtype, algo, ctas, a, s);
+    case TOK_BF16:
+      return launch_out<IN, __nv_bfloat16>(out_dtype, algo, ctas, a, s);
+    case TOK_F16:
+      return launch_out<IN, __half>(out_dtype, algo, ctas, a, s);
+  }
+  return static_cast<int>(cudaErrorInvalidValue);
+}
+
+}  // namespace
+
+size_t dtype_size(int dtype) { return dtype == TOK_F32 ? 4 : 2; }
+
+int pack_elems(int in_dtype, int wire_dtype, int out_dtype) {
+  return (in_dtype == TOK_F32 || wire_dtype == TOK_F32 || out_dtype == TOK_F32) ? 4 : 8;
+}
+
+int launch_allreduce(int algo, int in_dtype, int wire_dtype, int out_dtype, int ctas,
+                     const KArgs& args, void* stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch (in_dtype) {
+    case TOK_F32:
+      return launch_wire<float>(wire_dtype, out_dtype, algo, ctas, args, s);
+    case TOK_BF16:
+      return launch_wire<__nv_bfloat16>(wire_dtype, out_dtype, algo, ctas, args, s);
+    case TOK_F16:
+      return launch_wire<__half>(wire_dtype, out_dtype, algo, ctas, args, s);
+  }
+  return static_cast<int>(cudaErrorInvalidValue);
+}
+
+}  // namespace tok
