@@ -1,0 +1,95 @@
+"""DistributedDataParallel comm hook that routes every gradient bucket through libtok8s.
+
+Replaces, bucket by bucket, what the reference's torchjob does inside the user's container with
+PyTorch's default hook (`tensor.div_(N)` + `dist.all_reduce`,
+torch/distributed/algorithms/ddp_comm_hooks/default_hooks.py:18-33) or the compress hooks
+(`buffer.to(bf16).div_(N)` -> allreduce -> copy back, :57-92): one fused kernel does the cast, the
+1/N scale and the cross-replica sum over NVLink.  Hook contract: DistributedDataParallel
+.register_comm_hook (torch/nn/parallel/distributed.py:1987) — called on the autograd thread per
+bucket, must return a Future of the averaged bucket.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import torch
+
+from .comm import Communicator
+
+
+class BucketAllreduceHook:
+    """hook(state, bucket) -> Future[Tensor].
+
+    overlap=True launches on a dedicated communication stream so that the exchange of bucket k
+    overlaps the backward kernels that are still producing bucket k+1 (DDP's own overlap model);
+    the returned CUDA-aware Future carries the event consumers must wait on.
+    """
+
+    def __init__(self, comm: Communicator, *, wire_dtype: Optional[torch.dtype] = None,
+                 overlap: bool = True, record_events: bool = False, algo: int = 0):
+        self.comm = comm
+        self.wire_dtype = wire_dtype
+        self.overlap = overlap
+        self.algo = algo
+        self.record_events = record_events
+        self.events: List[Tuple[int, torch.cuda.Event, torch.cuda.Event]] = []
+        self._stream: Optional[torch.cuda.Stream] = None
+        self.buckets_seen = 0
+
+    def _comm_stream(self, device) -> torch.cuda.Stream:
+        if self._stream is None:
+            self._stream = torch.cuda.Stream(device=device, priority=-1)
+        return self._stream
+
+    def __call__(self, state, bucket):  # -> torch.futures.Future[torch.Tensor] (DDP checks the
+        # annotation object itself; `from __future__ import annotations` would stringify it)
+        buf = bucket.buffer()
+        if not buf.is_cuda:
+            raise RuntimeError("BucketAllreduceHook: gradient buckets must live on the replica's "
+                               "GPU; libtok8s has no CPU path")
+        world = self.comm.world
+        cur = torch.cuda.current_stream(buf.device)
+        stream = self._comm_stream(buf.device) if self.overlap else cur
+        if self.overlap:
+            stream.wait_stream(cur)  # the bucket's gradients were produced on `cur`
+        with torch.cuda.stream(stream):
+            if self.record_events:
+                e0 = torch.cuda.Event(enable_timing=True)
+                e1 = torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+            self.comm.allreduce_bucket(buf, buf, scale=1.0 / world, wire_dtype=self.wire_dtype,
+                                       algo=self.algo, stream=stream)
+            if self.record_events:
+                e1.record(stream)
+                wire = self.wire_dtype or buf.dtype
+                self.events.append((buf.numel() * torch.empty(0, dtype=wire).element_size(),
+                                    buf.numel() * buf.element_size(), e0, e1))
+            fut: torch.futures.Future = torch.futures.Future(devices=[buf.device])
+            # Safe before the kernel finishes: the future records an event on the current (comm)
+            # stream and consumers synchronise their streams with it (torch.futures.Future docs).
+            fut.set_result(buf)
+        self.buckets_seen += 1
+        return fut
+
+    def as_function(self):
+        """A plain function for DistributedDataParallel.register_comm_hook, which reads
+        hook.__name__ / hook.__qualname__ and inspects the signature (distributed.py:2062-2291)."""
+        def tok8s_bucket_allreduce_hook(state, bucket):
+            return self(state, bucket)
+        return tok8s_bucket_allreduce_hook
+
+    def drain_events(self):
+        """[(wire_bytes, bucket_bytes, milliseconds)] of the recorded launches; clears the list."""
+        out = []
+        for wire_bytes, bucket_bytes, e0, e1 in self.events:
+            e1.synchronize()
+            out.append((wire_bytes, bucket_bytes, e0.elapsed_time(e1)))
+        self.events = []
+        return out
+
+
+def register(ddp_model, comm: Communicator, **kwargs) -> BucketAllreduceHook:
+    """ddp_model.register_comm_hook(state=None, hook=BucketAllreduceHook(comm, ...))."""
+    hook = BucketAllreduceHook(comm, **kwargs)
+    ddp_model.register_comm_hook(None, hook.as_function())
+    return hook

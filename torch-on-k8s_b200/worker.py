@@ -1,0 +1,72 @@
+"""Replica-side entry: what a training script does instead of
+`torch.distributed.init_process_group(backend, "env://")` + `DistributedDataParallel(model)`.
+
+It consumes exactly the env contract the reference operator writes into every container
+(TorchJobReconciler.SetClusterSpec, controllers/train/torchjob_controller.go:394-446):
+MASTER_ADDR, MASTER_PORT, RANK, WORLD_SIZE — plus LOCAL_RANK / TOK8S_GPU for the GPU binding that
+the single-box controller assigns (one replica per GPU).
+"""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+from .comm import Communicator, default_rendezvous_path
+from .ddp_hook import BucketAllreduceHook
+
+
+@dataclass
+class Replica:
+    rank: int
+    world: int
+    device: torch.device
+    comm: Communicator
+    job_id: str
+
+    def wrap(self, model: torch.nn.Module, *, bucket_cap_mb: int = 25,
+             wire_dtype: Optional[torch.dtype] = None, overlap: bool = True,
+             record_events: bool = False, **ddp_kwargs):
+        """DistributedDataParallel(model) whose gradient buckets go through libtok8s."""
+        from torch.nn.parallel import DistributedDataParallel as DDP
+        ddp = DDP(model, device_ids=[self.device.index], bucket_cap_mb=bucket_cap_mb,
+                  gradient_as_bucket_view=True, **ddp_kwargs)
+        hook = BucketAllreduceHook(self.comm, wire_dtype=wire_dtype, overlap=overlap,
+                                   record_events=record_events)
+        ddp.register_comm_hook(None, hook.as_function())
+        return ddp, hook
+
+    def close(self):
+        self.comm.close()
+        if dist.is_initialized():
+            dist.destroy_process_group()
+
+
+def init_replica(job_id: Optional[str] = None, *, device: Optional[int] = None,
+                 bootstrap_backend: str = "nccl", max_world: int = 8) -> Replica:
+    """Read RANK / WORLD_SIZE / MASTER_* (reference env contract), bind this replica to its GPU,
+    join the job's peer group.  torch.distributed is initialised only as plumbing (DDP needs a
+    process group for its initial parameter broadcast); gradients never touch it."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("torch-on-k8s_b200 replicas need a CUDA GPU: there is no CPU fallback "
+                           "(the reference-style gloo job lives in oracle/gloo_torchjob.py)")
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "23456")  # TorchJobDefaultPort (constants.go:103)
+    if os.environ["MASTER_ADDR"] == "localhost":
+        os.environ["MASTER_ADDR"] = "127.0.0.1"
+    if device is None:
+        device = int(os.environ.get("TOK8S_GPU", os.environ.get("LOCAL_RANK", str(rank))))
+    torch.cuda.set_device(device)
+    dev = torch.device("cuda", device)
+    job_id = job_id or os.environ.get("TOK8S_JOB", "torchjob")
+    if not dist.is_initialized():
+        dist.init_process_group(bootstrap_backend, rank=rank, world_size=world, device_id=dev)
+    comm = Communicator(job_id, rank, world, device, max_world=max_world,
+                        rendezvous_path=os.environ.get("TOK8S_RDZV") or
+                        default_rendezvous_path(job_id))
+    return Replica(rank=rank, world=world, device=dev, comm=comm, job_id=job_id)
