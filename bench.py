@@ -108,7 +108,7 @@ def run_reference(args):
         return 0  # rank 0 alone runs the CPU job; other torchrun ranks exit without work
     from oracle import gloo_torchjob
     n = args.gpus
-    cores = os.cpu_count() or 1
+    cores = gloo_torchjob.effective_cores()
     batch = args.ref_batch
     t0 = time.time()
     res = gloo_torchjob.run("resnet50", world=n, steps=args.steps, warmup=args.warmup, batch=batch,

@@ -178,6 +178,14 @@ int tok_failover_decide(const char* restart_policy, int exit_code, const char* r
 int tok_job_update_status(tok_job_t* job, const char* replicas_json, int restarting,
                           const char* now_rfc3339, char** status_json);
 
+/* setCondition / filterOutCondition (pkg/utils/utils.go:186-243): append `type` (status True) unless
+ * the job is already Failed/Succeeded or the (status, reason) is unchanged; Running <-> Restarting
+ * evict each other; Failed/Succeeded flip Running to False.                                      */
+int tok_job_set_condition(tok_job_t* job, const char* type, const char* reason,
+                          const char* message, const char* now_rfc3339);
+/* NeedEnqueueToCoordinator (pkg/utils/utils.go:138-149).                                          */
+int tok_job_need_enqueue(const tok_job_t* job, int* need);
+
 /* Coordinator (pkg/coordinator/core/coordinator.go:164-476; RR/WRR core/policy.go:31-230; Quota
  * plugins/quota.go:82-277 over GPU slots; Priority plugins/priority.go:48-85).                   */
 typedef struct tok_coord tok_coord_t;

@@ -34,6 +34,25 @@ def free_port() -> int:
     return p
 
 
+def effective_cores() -> int:
+    """Host cores this container may actually use: min(affinity, cgroup cpu.max quota).  The GPU box
+    reports 128 logical CPUs but a 16-CPU quota; oversubscribing it makes OpenMP spin for minutes."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, int(float(quota) / float(period) + 0.5)))
+    except Exception:  # noqa: BLE001
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            p = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                n = min(n, max(1, (q + p - 1) // p))
+        except Exception:  # noqa: BLE001
+            pass
+    return max(1, n)
+
+
 def replica_env(job: str, task_type: str, index: int, num_workers: int, port: int = 23456,
                 local_master_addr: bool = True) -> Dict[str, str]:
     """Oracle restatement of the env half of SetClusterSpec (torchjob_controller.go:338-350,
@@ -145,7 +164,7 @@ def run(workload: str = "mlp", world: int = 2, steps: int = 5, warmup: int = 1, 
         job: str = "torchjob", timeout: float = 1800.0) -> dict:
     """Run the gloo/CPU torchjob with `world` replicas (1 master + world-1 workers) and return
     {"seconds", "steps", "images_per_sec", "cores", "threads_per_replica", "losses"}."""
-    cores = os.cpu_count() or 1
+    cores = effective_cores()
     threads = threads or max(1, cores // world)
     port = free_port()
     ctx = mp.get_context("spawn")
