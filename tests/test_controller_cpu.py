@@ -1,0 +1,116 @@
+"""The N>1 host path on CPU (world_size-2, gloo): the single-box controller admits, orders, wires and
+supervises replicas exactly as the reference operator would, and the job those replicas run
+reproduces the committed golden losses of the reference-style gloo torchjob."""
+import json
+import os
+import socket
+import sys
+
+import pytest
+
+from torch_on_k8s_b200.controller import Controller
+from torch_on_k8s_b200.sampler import ReplicaSampler
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = os.path.join(HERE, "golden")
+
+
+def free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def manifest(name, port, workers=1, queue=None, restart=None):
+    c = {"name": "torch", "image": "local", "command": [sys.executable, os.path.join(HERE, "cpu_replica.py")],
+         "ports": [{"name": "torchjob-port", "containerPort": port}]}
+    m = {"metadata": {"name": name, "namespace": "default"},
+         "spec": {"torchTaskSpecs": {"Master": {"template": {"spec": {"containers": [c]}}},
+                                     "Worker": {"numTasks": workers,
+                                                "template": {"spec": {"containers": [dict(c)]}}}}}}
+    if queue:
+        m["spec"]["schedulingPolicy"] = {"queue": queue}
+    if restart:
+        m["spec"]["torchTaskSpecs"]["Master"]["restartPolicy"] = restart
+    return m
+
+
+def test_mlp_torchjob_world2_matches_golden(tok_lib, tmp_path, monkeypatch):
+    monkeypatch.setenv("OUT_DIR", str(tmp_path))
+    ctl = Controller(num_gpus=2, log_dir=str(tmp_path / "logs"))
+    uid = ctl.submit(manifest("mnist", free_port()))
+    res = ctl.run_until_done(timeout=180)
+    assert res[uid] == "Succeeded", (res, ctl.events[-5:])
+    m = json.load(open(tmp_path / "mnist-master-0.json"))
+    w = json.load(open(tmp_path / "mnist-worker-0.json"))
+    assert (m["rank"], w["rank"], m["world"]) == (0, 1, 2)
+    assert m["env"]["PYTHONUNBUFFERED"] == "0" and m["env"]["TOK8S_GPU"] != w["env"]["TOK8S_GPU"]
+    gold = json.load(open(os.path.join(GOLD, "mlp_torchjob_n2", "run.json")))
+    assert m["losses"] == pytest.approx(gold["losses"][:2], rel=0, abs=0)   # bit-identical floats
+    reasons = [e[2] for e in ctl.events]
+    assert reasons.index("JobEnqueued") < reasons.index("JobDequeued") < reasons.index("GangAdmitted")
+    # DAG: the master is created before the worker
+    pods = [e[3] for e in ctl.events if e[2] == "SuccessfulCreatePod"]
+    assert pods[:2] == ["mnist-master-0", "mnist-worker-0"]
+    st = ctl.jobs[uid].job.status
+    assert st["taskStatuses"]["Master"]["succeed"] == 1 and st["taskStatuses"]["Worker"]["succeed"] == 1
+    assert len(ctl.free_gpus) == 2
+
+
+def test_two_queued_jobs_gang_on_two_slots(tok_lib, tmp_path, monkeypatch):
+    """BASELINE config 3 in miniature: two jobs of 2 replicas each on a 2-slot box — the second is
+    held in its queue until the first releases its slots (all-or-nothing MinMember)."""
+    monkeypatch.setenv("OUT_DIR", str(tmp_path))
+    ctl = Controller(num_gpus=2)
+    a = ctl.submit(manifest("ja", free_port(), queue="qa"))
+    b = ctl.submit(manifest("jb", free_port(), queue="qb"))
+    res = ctl.run_until_done(timeout=240)
+    assert res == {a: "Succeeded", b: "Succeeded"}
+    creates = [(e[0], e[3]) for e in ctl.events if e[2] == "SuccessfulCreatePod"]
+    first = creates[0][1][:2]
+    other = "jb" if first == "ja" else "ja"
+    done_first = [e[0] for e in ctl.events if e[2] == "ExitedWithCode" and e[3].startswith(first)]
+    start_other = [t for t, n in creates if n.startswith(other)]
+    assert min(start_other) >= min(done_first)   # never more than 2 replicas on 2 slots
+
+
+def test_failover_restarts_same_rank(tok_lib, tmp_path, monkeypatch):
+    """Master exits 137 (SIGKILL, retryable under restartPolicy ExitCode): it is recreated with the
+    same index => same RANK, the job goes through Restarting and still succeeds."""
+    monkeypatch.setenv("OUT_DIR", str(tmp_path))
+    monkeypatch.setenv("FAIL_ONCE", str(tmp_path / "failed.flag"))
+    monkeypatch.setenv("FAIL_CODE", "137")
+    ctl = Controller(num_gpus=2)
+    uid = ctl.submit(manifest("fo", free_port()))
+    res = ctl.run_until_done(timeout=240)
+    reasons = [e[2] for e in ctl.events]
+    assert "FailoverRecreate" in reasons
+    assert res[uid] == "Succeeded", ctl.events[-6:]
+    assert json.load(open(tmp_path / "fo-master-0.json"))["rank"] == 0
+
+
+def test_permanent_exit_code_fails_job(tok_lib, tmp_path, monkeypatch):
+    monkeypatch.setenv("OUT_DIR", str(tmp_path))
+    monkeypatch.setenv("FAIL_ONCE", str(tmp_path / "failed.flag"))
+    monkeypatch.setenv("FAIL_CODE", "1")      # permanent under ExitCode (failover.go:64-76)
+    ctl = Controller(num_gpus=2)
+    uid = ctl.submit(manifest("pf", free_port()))
+    res = ctl.run_until_done(timeout=120)
+    assert res[uid] == "Failed"
+
+
+def test_replica_sampler_matches_distributed_sampler_goldens():
+    cases = json.load(open(os.path.join(GOLD, "sampler.json")))
+    for c in cases:
+        for r in range(c["world"]):
+            s = ReplicaSampler(c["n"], c["world"], r, shuffle=c["shuffle"], seed=c["seed"],
+                               drop_last=c["drop_last"])
+            s.set_epoch(c["epoch"])
+            assert list(s) == c["indices"][r]          # bit-exact indices
+    s = ReplicaSampler(100, 4, 1, seed=3)
+    before = s.indices()
+    s.reform(8, 5)
+    t = ReplicaSampler(100, 8, 5, seed=3)
+    assert s.indices() == t.indices() and s.indices() != before

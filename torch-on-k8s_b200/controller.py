@@ -1,0 +1,284 @@
+"""Single-box TorchJob controller: the reference operator's reconcile loop for the data-parallel
+path, with "pod" = OS process bound to one GPU of the 8xB200 box.
+
+  reference                                            here
+  -------------------------------------------------    ------------------------------------------------
+  OnOwnerCreateFunc: default, Created, enqueue         submit(): TorchJob defaults, Created, coordinator
+    (controllers/common/eventhandler.go:38-64)           .enqueue (held until dequeued — §2.3 intent)
+  Coordinator.schedule every 100 ms                     tick(): Coordinator.tick (C ABI)
+    (pkg/coordinator/core/coordinator.go:310-366)
+  ReconcileJobs: PodGroup, DAG order, ReconcilePods     _reconcile(): gang admission over free GPU slots
+    (controllers/common/job.go:55-342)                   (all-or-nothing MinMember), AIMaster -> Master
+                                                         -> Worker with the DAG gate, one process per
+                                                         missing index
+  createNewPod + SetClusterSpec                         _start_replica(): env from tok_job_cluster_spec
+    (controllers/common/pod.go:503-637)                  + TOK8S_GPU / TOK8S_JOB / TOK8S_RDZV
+  reconcileOnePod + failover table                      _poll(): exit codes -> should_failover ->
+    (pod.go:640-687, failover.go:52-172)                 restart same index (same RANK), Restarting
+  updateGeneralJobStatus                                TorchJob.update_status (C ABI)
+
+All decisions are made by libtok8s' C++ control plane through the C ABI; this module only owns the
+processes.  Nothing here touches the data path.
+"""
+from __future__ import annotations
+
+import os
+import shlex
+import signal
+import subprocess
+import sys
+import time
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional
+
+from .coordinator import SCHEDULING_PERIOD_S, Coordinator
+from .job import TASK_ORDER, TorchJob, should_failover
+
+
+def _now() -> str:
+    return time.strftime("%Y-%m-%dT%H:%M:%SZ", time.gmtime())
+
+
+@dataclass
+class ReplicaProc:
+    task_type: str
+    index: int
+    gpu: Optional[int]
+    proc: Optional[subprocess.Popen] = None
+    phase: str = "Pending"      # Pending | Running | Succeeded | Failed
+    exit_code: Optional[int] = None
+    restarts: int = 0
+    log_path: Optional[str] = None
+
+
+@dataclass
+class ManagedJob:
+    job: TorchJob
+    uid: str
+    command: Optional[List[str]] = None
+    replicas: Dict[str, Dict[int, ReplicaProc]] = field(default_factory=dict)
+    admitted: bool = False
+    dequeued: bool = False
+    gpus: List[int] = field(default_factory=list)
+    done: bool = False
+
+
+class Controller:
+    def __init__(self, num_gpus: int = 8, *, policy: str = "wrr", log_dir: Optional[str] = None,
+                 rdzv_dir: str = "/tmp"):
+        self.free_gpus = list(range(num_gpus))
+        self.num_gpus = num_gpus
+        self.coord = Coordinator(policy=policy)
+        self.coord.set_quota("", num_gpus)      # the box is the (only) quota
+        self.jobs: Dict[str, ManagedJob] = {}
+        self.log_dir = log_dir
+        self.rdzv_dir = rdzv_dir
+        self.events: List[tuple] = []
+
+    # ---- submit (owner create) -------------------------------------------------------------------
+    def submit(self, manifest, command: Optional[List[str]] = None) -> str:
+        job = manifest if isinstance(manifest, TorchJob) else TorchJob(manifest)
+        d = job.to_dict()
+        uid = d["metadata"].get("uid") or "%s/%s" % (d["metadata"].get("namespace", "default"),
+                                                       d["metadata"]["name"])
+        job.set_condition("Created", "JobCreated", "TorchJob %s is created." % job.name, _now())
+        mj = ManagedJob(job=job, uid=uid, command=command)
+        self.jobs[uid] = mj
+        if job.need_enqueue():
+            self.coord.enqueue(job, uid)
+            job.set_condition("Queuing", "JobEnqueued",
+                              "Job %s is queuing and waiting for being scheduled." % uid, _now())
+        self._event(uid, "JobEnqueued")
+        return uid
+
+    def _event(self, uid, reason, msg=""):
+        self.events.append((time.time(), uid, reason, msg))
+
+    # ---- one controller pass ------------------------------------------------------------------------
+    def tick(self, now: Optional[float] = None) -> None:
+        now = time.monotonic() if now is None else now
+        used = self.num_gpus - len(self.free_gpus)
+        for tenant in {self._tenant(m) for m in self.jobs.values()}:
+            self.coord.set_used(tenant, 0)
+        self.coord.set_used("", used)
+        out = self.coord.tick(now)
+        if out.get("dequeued"):
+            mj = self.jobs[out["dequeued"]]
+            mj.dequeued = True
+            mj.job.set_condition("Queuing", "JobDequeued",
+                                 "Job %s is being dequeued and waiting for reconciling." % mj.uid, _now())
+            self._event(mj.uid, "JobDequeued")
+        for mj in list(self.jobs.values()):
+            if mj.dequeued and not mj.done:
+                self._reconcile(mj)
+
+    @staticmethod
+    def _tenant(mj: ManagedJob) -> str:
+        d = mj.job.to_dict()
+        return (d["spec"].get("schedulingPolicy") or {}).get("queue") or \
+            d["metadata"].get("namespace", "default")
+
+    # ---- reconcile -------------------------------------------------------------------------------------
+    def _reconcile(self, mj: ManagedJob) -> None:
+        job = mj.job
+        if not mj.admitted:
+            g = job.gang_admit(len(self.free_gpus))
+            if not g["admitted"]:
+                return  # all-or-nothing: wait for MinMember slots
+            mj.admitted = True
+            self._event(mj.uid, "GangAdmitted", "slots=%d" % g["slotsNeeded"])
+        restarting = self._poll(mj)
+        specs = job.task_specs
+        for tt in TASK_ORDER + [k for k in specs if k not in TASK_ORDER]:
+            if tt not in specs:
+                continue
+            phases = {k: [r.phase for r in v.values()] for k, v in mj.replicas.items()}
+            if not job.dag_ready(tt, phases):
+                continue
+            have = mj.replicas.setdefault(tt, {})
+            for idx in range(int(specs[tt].get("numTasks", 1))):
+                if idx not in have:
+                    self._start_replica(mj, tt, idx)
+        reps = {tt: [dict(phase=r.phase, scheduled=r.gpu is not None or tt == "AIMaster",
+                          exitCode=r.exit_code) for r in v.values()]
+                for tt, v in mj.replicas.items()}
+        job.update_status(reps, restarting, _now())
+        last = job.last_condition()
+        if last in ("Running", "Failed", "Succeeded"):
+            self.coord.job_settled(mj.uid)
+        if last in ("Failed", "Succeeded"):
+            self._finish(mj)
+
+    def _start_replica(self, mj: ManagedJob, tt: str, idx: int, restarts: int = 0) -> None:
+        spec = mj.job.cluster_spec(tt.lower(), idx)
+        gpu = None
+        if spec["gpuSlots"] > 0:
+            if not self.free_gpus:
+                mj.replicas[tt][idx] = ReplicaProc(tt, idx, None)   # Pending, unscheduled
+                return
+            gpu = self.free_gpus.pop(0)
+            mj.gpus.append(gpu)
+        env = dict(os.environ)
+        env.update({e["name"]: e["value"] for e in spec["env"]})
+        if env.get("MASTER_ADDR") not in ("localhost", "127.0.0.1"):
+            env["MASTER_ADDR"] = "127.0.0.1"   # single box: the master's name resolves to loopback
+        env.update(TOK8S_JOB=mj.job.name, TOK8S_REPLICA=spec["name"], TOK8S_TASK_TYPE=tt,
+                   TOK8S_TASK_INDEX=str(idx),
+                   TOK8S_RDZV=os.path.join(self.rdzv_dir, "tok8s-%s-%s" %
+                                           (mj.job.name.replace("/", "-"), env["MASTER_PORT"])))
+        if gpu is not None:
+            env.update(TOK8S_GPU=str(gpu), LOCAL_RANK=str(gpu))
+        cmd = mj.command or self._container_command(mj, tt)
+        cmd = list(cmd) + spec["args"] if spec["args"] and mj.command is None else list(cmd)
+        log = None
+        if self.log_dir:
+            os.makedirs(self.log_dir, exist_ok=True)
+            path = os.path.join(self.log_dir, spec["name"] + ".log")
+            log = open(path, "ab")
+        proc = subprocess.Popen(cmd, env=env, stdout=log or None, stderr=subprocess.STDOUT if log else None,
+                                start_new_session=True)
+        mj.replicas[tt][idx] = ReplicaProc(tt, idx, gpu, proc, "Running", restarts=restarts,
+                                           log_path=log.name if log else None)
+        self._event(mj.uid, "SuccessfulCreatePod", spec["name"])
+
+    def _container_command(self, mj: ManagedJob, tt: str) -> List[str]:
+        c = None
+        for cand in mj.job.task_specs[tt].get("template", {}).get("spec", {}).get("containers", []):
+            if cand.get("name") == "torch":
+                c = cand
+        if not c or not (c.get("command") or c.get("args")):
+            raise ValueError("replica template of %s has no `torch` container command" % tt)
+        return list(c.get("command") or []) + list(c.get("args") or [])
+
+    def _poll(self, mj: ManagedJob) -> bool:
+        """reconcileOnePod for every replica; returns True when a failover was triggered."""
+        restarting = False
+        for tt, reps in mj.replicas.items():
+            policy = mj.job.task_specs[tt].get("restartPolicy", "")
+            for idx, r in list(reps.items()):
+                if r.proc is None:
+                    if r.gpu is None and self.free_gpus and r.phase == "Pending":
+                        del reps[idx]          # a GPU slot freed up: recreate the replica
+                    continue
+                rc = r.proc.poll()
+                if rc is None or r.phase in ("Succeeded", "Failed"):
+                    continue
+                code = rc if rc >= 0 else 128 - rc     # killed by signal n -> 128 + n
+                r.exit_code = code
+                r.phase = "Succeeded" if code == 0 else "Failed"
+                self._release(mj, r)
+                self._event(mj.uid, "ExitedWithCode", "%s-%s-%d: %d" % (mj.job.name, tt, idx, code))
+                if code != 0 and should_failover(policy, code, ""):
+                    del reps[idx]              # recreated next pass with the same index => same RANK
+                    restarting = True
+                    self._event(mj.uid, "FailoverRecreate", "%s-%d" % (tt, idx))
+                elif code != 0 and policy in ("OnFailure", "Always"):
+                    limit = (mj.job.to_dict()["spec"].get("backoffLimit"))
+                    if limit is None or r.restarts < int(limit):
+                        n = r.restarts + 1
+                        del reps[idx]
+                        self._start_replica(mj, tt, idx, restarts=n)   # kubelet-style in-place restart
+        return restarting
+
+    def _release(self, mj: ManagedJob, r: ReplicaProc) -> None:
+        if r.gpu is not None and r.gpu in mj.gpus:
+            mj.gpus.remove(r.gpu)
+            self.free_gpus.append(r.gpu)
+            self.free_gpus.sort()
+            r.gpu = None
+
+    def _finish(self, mj: ManagedJob) -> None:
+        policy = mj.job.to_dict()["spec"].get("clenPodPolicy", "None")
+        for reps in mj.replicas.values():
+            for r in reps.values():
+                if r.proc and r.proc.poll() is None and policy == "Running":
+                    try:
+                        os.killpg(r.proc.pid, signal.SIGTERM)
+                    except ProcessLookupError:
+                        pass
+                if r.proc and r.proc.poll() is not None:
+                    self._release(mj, r)
+        mj.done = True
+        self._event(mj.uid, "Job" + (mj.job.last_condition() or ""))
+
+    # ---- helpers ------------------------------------------------------------------------------------------
+    def run_until_done(self, timeout: float = 600.0, period: float = SCHEDULING_PERIOD_S) -> Dict[str, str]:
+        deadline = time.time() + timeout
+        while time.time() < deadline and not all(m.done for m in self.jobs.values()):
+            self.tick()
+            time.sleep(period)
+        for mj in self.jobs.values():
+            if not mj.done:
+                for reps in mj.replicas.values():
+                    for r in reps.values():
+                        if r.proc and r.proc.poll() is None:
+                            try:
+                                os.killpg(r.proc.pid, signal.SIGKILL)
+                            except ProcessLookupError:
+                                pass
+        return {uid: (m.job.last_condition() or "") for uid, m in self.jobs.items()}
+
+
+def main(argv=None) -> int:
+    import argparse
+    import json
+    from .job import load_manifest
+    ap = argparse.ArgumentParser(prog="tok8s-controller",
+                                 description="run TorchJob manifests on this box (one replica per GPU)")
+    ap.add_argument("manifests", nargs="+")
+    ap.add_argument("--gpus", type=int, default=8)
+    ap.add_argument("--policy", default="wrr", choices=["rr", "wrr"])
+    ap.add_argument("--command", default=None, help="override the replica command (shell-split)")
+    ap.add_argument("--log-dir", default=None)
+    ap.add_argument("--timeout", type=float, default=3600)
+    a = ap.parse_args(argv)
+    ctl = Controller(a.gpus, policy=a.policy, log_dir=a.log_dir)
+    for m in a.manifests:
+        ctl.submit(load_manifest(m), shlex.split(a.command) if a.command else None)
+    res = ctl.run_until_done(a.timeout)
+    print(json.dumps(res))
+    return 0 if all(v == "Succeeded" for v in res.values()) else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())
