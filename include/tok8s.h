@@ -128,6 +128,11 @@ int tok_allreduce_algo(tok_comm_t* comm, size_t wire_bytes, int* algo);
 /* Number of kernels this communicator has launched so far (bench.py's gpu_launches). */
 int tok_comm_launches(tok_comm_t* comm, uint64_t* launches);
 
+/* Profiling aid: with TOK_DEBUG_PHASES=1 in the environment at tok_comm_create, every exchange
+ * kernel records per-CTA globaltimer stamps [cta][8] = {start, staged, barrierA, reduced, barrierB,
+ * end}; this copies the last launch's stamps to the host (synchronises).                       */
+int tok_comm_debug_read(tok_comm_t* comm, uint64_t* out, size_t words);
+
 /* ---- control plane (TorchJob surface) ------------------------------------------------------
  * JSON in, JSON out.  `tok_job_t` is a parsed + defaulted TorchJob (apis/train/v1alpha1).        */
 

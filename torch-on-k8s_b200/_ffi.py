@@ -88,6 +88,7 @@ PROTOTYPES = {
                                        C.c_float, C.c_uint, _P]),
     "tok_allreduce_algo": (C.c_int, [_P, C.c_size_t, _IP]),
     "tok_comm_launches": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
+    "tok_comm_debug_read": (C.c_int, [_P, C.POINTER(C.c_uint64), C.c_size_t]),
     "tok_set_feature_gates": (C.c_int, [C.c_uint]),
     "tok_get_feature_gates": (C.c_uint, []),
     "tok_job_parse": (C.c_int, [_S, _PP]),

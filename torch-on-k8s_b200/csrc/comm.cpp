@@ -351,13 +351,15 @@ struct tok_comm {
   CUmemGenericAllocationHandle mc_handle = 0;
   CUdeviceptr mc_va = 0;
 
+  unsigned long long* dbg = nullptr;    // device, only with TOK_DEBUG_PHASES=1
   uint32_t* ctr = nullptr;              // device
   volatile uint32_t* hostctl = nullptr; // pinned host page
   uint32_t* hostctl_dev = nullptr;
 
   // tunables
-  int max_ctas = 64;
-  size_t cta_bytes = 65536;
+  int max_ctas = 96;
+  size_t cta_bytes = 32768;
+  size_t chunk_packs_max = 4096;
   size_t one_shot_max = 256 << 10;
   size_t nvls_min = 1 << 20;
   int force_algo = 0;
@@ -472,6 +474,10 @@ int alloc_local(tok_comm* c) {
   RT_CHECK(cudaMemset(reinterpret_cast<void*>(c->local_va), 0, kFlagBytes));
   RT_CHECK(cudaMalloc(reinterpret_cast<void**>(&c->ctr), kCtrWords * sizeof(uint32_t)));
   RT_CHECK(cudaMemset(c->ctr, 0, kCtrWords * sizeof(uint32_t)));
+  if (env_size("TOK_DEBUG_PHASES", 0)) {
+    RT_CHECK(cudaMalloc(reinterpret_cast<void**>(&c->dbg), kMaxCtas * 8 * sizeof(unsigned long long)));
+    RT_CHECK(cudaMemset(c->dbg, 0, kMaxCtas * 8 * sizeof(unsigned long long)));
+  }
   void* hp = nullptr;
   RT_CHECK(cudaHostAlloc(&hp, 4096, cudaHostAllocMapped | cudaHostAllocPortable));
   memset(hp, 0, 4096);
@@ -830,9 +836,14 @@ int create_impl(const char* job_id, int rank, int world, int max_world, int devi
            static_cast<uint64_t>(now_s() * 1e6);
   if (c->uid == 0) c->uid = 1;
   c->cap_bytes = round_up(env_size("TOK_STAGING_MB", 128) << 20, 2u << 20);
-  c->max_ctas = static_cast<int>(std::min<size_t>(env_size("TOK_MAX_CTAS", 64), kMaxCtas));
+  c->max_ctas = static_cast<int>(std::min<size_t>(env_size("TOK_MAX_CTAS", 96), kMaxCtas));
   if (c->max_ctas < 1) c->max_ctas = 1;
-  c->cta_bytes = std::max<size_t>(env_size("TOK_CTA_BYTES", 65536), 4096);
+  c->cta_bytes = std::max<size_t>(env_size("TOK_CTA_BYTES", 32768), 4096);
+  {
+    size_t cp = env_size("TOK_CHUNK_PACKS", 4096), p2 = kThreads;
+    while (p2 * 2 <= cp && p2 < 65536) p2 *= 2;  // power-of-two multiple of kThreads
+    c->chunk_packs_max = p2;
+  }
   c->one_shot_max = env_size("TOK_ONE_SHOT_MAX", 256 << 10);
   c->nvls_min = env_size("TOK_NVLS_MIN", 1 << 20);
   c->force_algo = static_cast<int>(env_size("TOK_ALGO", 0));
@@ -955,6 +966,7 @@ int tok_comm_destroy(tok_comm_t* c) {
     c->cache.clear();
     if (c->local_handle) drv().cuMemRelease_(c->local_handle);
     if (c->ctr) cudaFree(c->ctr);
+    if (c->dbg) cudaFree(c->dbg);
     if (c->hostctl) cudaFreeHost(const_cast<uint32_t*>(c->hostctl));
     cudaGetLastError();
   }
@@ -985,6 +997,15 @@ int tok_comm_caps(tok_comm_t* c, tok_caps_t* caps) {
 int tok_allreduce_algo(tok_comm_t* c, size_t wire_bytes, int* algo) {
   if (!c || !algo) return fail(TOK_ERR_INVALID, "comm / algo is null");
   *algo = pick_algo(c, wire_bytes);
+  return TOK_OK;
+}
+
+int tok_comm_debug_read(tok_comm_t* c, uint64_t* out, size_t words) {
+  if (!c || !out) return fail(TOK_ERR_INVALID, "comm / out is null");
+  if (!c->dbg) return fail(TOK_ERR_STATE, "phase timestamps are off (set TOK_DEBUG_PHASES=1 before tok_comm_create)");
+  const size_t n = std::min<size_t>(words, kMaxCtas * 8);
+  DeviceGuard guard(c->device);
+  RT_CHECK(cudaMemcpy(out, c->dbg, n * sizeof(uint64_t), cudaMemcpyDeviceToHost));
   return TOK_OK;
 }
 
@@ -1041,6 +1062,7 @@ int tok_allreduce_bucket(tok_comm_t* c, const void* in, void* out, size_t count,
   a.ctr = c->ctr;
   a.hostctl = c->hostctl_dev;
   a.timeout_ns = c->barrier_timeout_ns;
+  a.dbg = c->dbg;
   a.scale = scale;
   a.rank = c->rank;
   a.world = c->world;
@@ -1056,15 +1078,20 @@ int tok_allreduce_bucket(tok_comm_t* c, const void* in, void* out, size_t count,
     if (algo == TOK_ALGO_LOCAL) {
       const size_t want = (a.total_packs + kThreads * 4 - 1) / (kThreads * 4);
       ctas = static_cast<int>(std::min<size_t>(std::max<size_t>(want, 1), c->sm_count * 4));
-      a.packs_per_cta = 0;
+      a.chunk_packs = 0;
+      a.shard_packs = 0;
     } else {
+      // NVLink phases are cut into chunks of C packs claimed dynamically by the rank's CTAs; aim at
+      // >= 2 chunks per CTA in the shard phase, between 512 packs (one per thread) and 4096 (64 KiB).
+      const size_t per = (algo == TOK_ALGO_ONE_SHOT) ? a.total_packs
+                                                      : (a.total_packs + c->world - 1) / c->world;
+      size_t C = c->chunk_packs_max;
+      while (C > static_cast<size_t>(kThreads) && per < C * 2 * static_cast<size_t>(c->max_ctas)) C >>= 1;
+      a.chunk_packs = C;
+      a.shard_packs = round_up(per, C);
       const size_t bytes = a.total_packs * P * wsz;
-      size_t g = std::min<size_t>(std::max<size_t>((bytes + c->cta_bytes - 1) / c->cta_bytes, 1),
-                                  c->max_ctas);
-      size_t L = (a.total_packs + g - 1) / g;
-      if (algo != TOK_ALGO_ONE_SHOT) L = round_up(L, c->world);
-      a.packs_per_cta = L;
-      ctas = static_cast<int>((a.total_packs + L - 1) / L);
+      const size_t by_bytes = (bytes + c->cta_bytes - 1) / c->cta_bytes;
+      ctas = static_cast<int>(std::min<size_t>(std::max<size_t>(by_bytes, 1), c->max_ctas));
     }
     int e = launch_allreduce(algo, in_dtype, wire_dtype, out_dtype, ctas, a, cuda_stream);
     if (e != 0)
