@@ -278,6 +278,52 @@ def run_ours(args):
                         "(includes waiting for the slowest replica to reach the bucket); NVLS may "
                         "exceed 1.0"}
 
+    # ---- the same buckets, exchanged back to back with nothing else on the GPU (kernel quality
+    #      without the wait for the slowest replica's backward); buffers rotate over > L2 bytes ------
+    sizes = [e[0] for e in ev[:max(1, len(ev) // args.steps)]]
+    iso = None
+    if sizes:
+        el = torch.empty(0, dtype=torch.bfloat16).element_size()
+        nsets = max(2, int((160 << 20) / max(sum(sizes), 1)) + 1)
+        sets = [[torch.randn(sz // el, device=dev).to(torch.bfloat16) for sz in sizes]
+                for _ in range(min(nsets, 8))]
+        cstream = torch.cuda.Stream(device=dev)
+
+        def iso_step(i):
+            for t in sets[i % len(sets)]:
+                rep.comm.allreduce_bucket(t, t, scale=1.0 / world, stream=cstream)
+
+        with torch.cuda.stream(cstream):
+            for i in range(5):
+                iso_step(i)
+            cstream.synchronize()
+            barrier()
+            i0 = torch.cuda.Event(enable_timing=True)
+            i1 = torch.cuda.Event(enable_timing=True)
+            iters = 30
+            i0.record(cstream)
+            for i in range(iters):
+                iso_step(i)
+            i1.record(cstream)
+            cstream.synchronize()
+        tt = torch.tensor([i0.elapsed_time(i1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        iso_ms = float(tt.item())
+        iso_bytes = float(sum(sizes) * iters)
+        if world == 1:
+            ach = 2.0 * iso_bytes / (iso_ms * 1e-3) / 1e9
+            iso = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                   "frac": ach / peaks["hbm_gbs"], "avg_launch_us": iso_ms * 1e3 / (iters * len(sizes))}
+        else:
+            ach = iso_bytes / (iso_ms * 1e-3) / 1e9 * 2.0 * (world - 1) / world
+            iso = {"bound": "nvlink", "achieved": ach, "peak": NVLINK_PEAK_GBS, "unit": "GB/s",
+                   "frac": ach / NVLINK_PEAK_GBS, "avg_launch_us": iso_ms * 1e3 / (iters * len(sizes))}
+        iso["bucket_bytes"] = sizes
+        iso["note"] = ("the step's buckets exchanged back to back on an otherwise idle GPU, inputs "
+                       "rotated over >126 MB so they are not L2 resident")
+        rep.comm.status()
+
     if rank != 0:
         rep.close()
         return 0
@@ -301,6 +347,7 @@ def run_ours(args):
                 "d2h_bytes_per_step": 4 * world, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches * world),
         "roofline": roof,
+        "roofline_isolated": iso,
     }
     if world == 1 and not args.no_cpu_baseline:
         # bounded sample of the same workload on the host cores: the reference-style gloo job

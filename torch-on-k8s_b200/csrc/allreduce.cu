@@ -221,59 +221,21 @@ TOK_MM_16BIT(__half, "f16x2")
 #undef TOK_MM_16BIT
 
 // ------------------------------------------------------------------------------------------------
-// Rank-level cross-replica barrier + dynamic work distribution.
-//
-// Every phase of an exchange kernel is a list of fixed-size chunks of 16-byte packs that the rank's
-// CTAs claim from an atomic counter (the next claim is issued while the current chunk is processed),
-// so SMs that see less NVLink/HBM bandwidth simply take fewer chunks and the phase ends when the
-// RANK is done, not when its slowest pre-assigned CTA is.  A phase boundary is then:
-//   each CTA: bar.sync; fence.sys; ticket = atomicAdd(phase ticket)
-//   the CTA that draws the last ticket publishes `target` into flag[rank] of every replica's heap
-//     (st.release.sys — cumulative over the other CTAs' fenced writes)
-//   every CTA spins (ld.acquire.sys) on flag[0..world) of its OWN heap until all reached `target`.
-// Flag values only grow (one word per source rank); a replica can be at most one barrier ahead.
-// Spinning gives up on host abort or after timeout_ns: a dead peer must not hang the GPU.
+// Per-CTA cross-replica barrier.  CTA b of rank r publishes `target` into flag[b][r] of every
+// replica (release, system scope) and waits until flag[b][p] of its own heap reached `target` for
+// every p (acquire).  Values only grow; a replica can be at most one barrier ahead, so one flag word
+// per (CTA, source) suffices.  Gives up on host abort or after timeout_ns (a dead peer must not
+// hang the GPU).
 // ------------------------------------------------------------------------------------------------
-struct Sync {
-  uint32_t seq;  // launches completed before this one (staging-buffer parity)
-  uint32_t bar;  // barriers completed before this launch
-};
-
-// Optional phase timestamps for tools/phase_breakdown.py (never enabled on the product path).
-__device__ __forceinline__ void dbg_stamp(const KArgs& a, int slot) {
-  if (a.dbg != nullptr && threadIdx.x == 0) a.dbg[blockIdx.x * 8 + slot] = globaltimer_ns();
-}
-
-__device__ __forceinline__ Sync sync_begin(const KArgs& a, uint32_t* s_words, int* s_fail) {
-  if (threadIdx.x == 0) {
-    s_words[0] = a.ctr[kCtrCallSeq];
-    s_words[1] = a.ctr[kCtrBar];
-    *s_fail = 0;
-  }
-  __syncthreads();
-  Sync st;
-  st.seq = s_words[0];
-  st.bar = s_words[1];
-  return st;
-}
-
-__device__ __forceinline__ bool rank_barrier(const KArgs& a, int phase, uint32_t target,
-                                             int* s_last, int* s_fail) {
+__device__ __forceinline__ bool cta_barrier(const KArgs& a, uint32_t target, int* s_fail) {
   __syncthreads();
   const int t = threadIdx.x;
-  if (t == 0) {
-    __threadfence_system();  // this CTA's staged/reduced packs are visible system-wide
-    const unsigned ticket = atomicAdd(&a.ctr[kCtrTicket + phase], 1u);
-    *s_last = (ticket == gridDim.x - 1) ? 1 : 0;
-  }
-  __syncthreads();
   if (t < a.world) {
-    if (*s_last) {
-      __threadfence_system();
-      uint32_t* remote = reinterpret_cast<uint32_t*>(a.peer[t]) + a.rank;
-      st_release_sys(remote, target);
-    }
-    const uint32_t* mine = reinterpret_cast<const uint32_t*>(a.peer[a.rank]) + t;
+    uint32_t* remote =
+        reinterpret_cast<uint32_t*>(a.peer[t]) + (blockIdx.x * kMaxWorld + a.rank);
+    st_release_sys(remote, target);
+    const uint32_t* mine =
+        reinterpret_cast<const uint32_t*>(a.peer[a.rank]) + (blockIdx.x * kMaxWorld + t);
     unsigned long long t0 = 0;
     uint32_t spins = 0;
     while (static_cast<int32_t>(ld_acquire_sys(mine) - target) < 0) {
@@ -298,60 +260,47 @@ __device__ __forceinline__ bool rank_barrier(const KArgs& a, int phase, uint32_t
   return *s_fail == 0;
 }
 
-// Last CTA out resets the per-launch counters, bumps the launch sequence (selects the other staging
-// buffer next time) and the barrier count.  Nothing about the sequence lives on the host, so the
-// launch can be captured in a CUDA graph and replayed.
-__device__ __forceinline__ void sync_end(const KArgs& a, const Sync& st, uint32_t barriers) {
+// Optional phase timestamps for tools/phase_breakdown.py (never enabled on the product path).
+__device__ __forceinline__ void dbg_stamp(const KArgs& a, int slot) {
+  if (a.dbg != nullptr && threadIdx.x == 0) a.dbg[blockIdx.x * 8 + slot] = globaltimer_ns();
+}
+
+struct CtaState {
+  uint32_t seq;   // launches completed before this one (buffer parity)
+  uint32_t bar;   // barriers this CTA index has passed
+};
+
+__device__ __forceinline__ CtaState cta_begin(const KArgs& a, uint32_t* s_words, int* s_fail) {
+  if (threadIdx.x == 0) {
+    s_words[0] = a.ctr[kCtrCallSeq];
+    s_words[1] = a.ctr[blockIdx.x];
+    *s_fail = 0;
+  }
+  __syncthreads();
+  CtaState st;
+  st.seq = s_words[0];
+  st.bar = s_words[1];
+  return st;
+}
+
+// Last CTA out bumps the launch sequence (selects the other staging buffer next time); works under
+// CUDA-graph replay because nothing about the sequence lives on the host.
+__device__ __forceinline__ void cta_end(const KArgs& a, const CtaState& st) {
   __syncthreads();
   if (threadIdx.x == 0) {
+    a.ctr[blockIdx.x] = st.bar;
     __threadfence();
     const unsigned ticket = atomicAdd(&a.ctr[kCtrDone], 1u);
     if (ticket == gridDim.x - 1) {
-      for (int k = 0; k < 3; ++k) {
-        a.ctr[kCtrTicket + k] = 0;
-        a.ctr[kCtrWork + k] = 0;
-      }
       a.ctr[kCtrDone] = 0;
-      a.ctr[kCtrBar] = st.bar + barriers;
       a.ctr[kCtrCallSeq] = st.seq + 1;
     }
-  }
-}
-
-// Dynamic chunk loop: calls fn(chunk) for chunk ids claimed from ctr[kCtrWork + phase] until the
-// phase's `nchunks` are exhausted.  The next id is claimed before the current chunk is processed.
-template <class F>
-__device__ __forceinline__ void for_each_chunk(const KArgs& a, int phase, size_t nchunks,
-                                               unsigned* s_next, F fn) {
-  if (threadIdx.x == 0) *s_next = atomicAdd(&a.ctr[kCtrWork + phase], 1u);
-  __syncthreads();
-  for (;;) {
-    const size_t c = *s_next;
-    __syncthreads();
-    if (c >= nchunks) break;
-    if (threadIdx.x == 0) *s_next = atomicAdd(&a.ctr[kCtrWork + phase], 1u);
-    fn(c);
-    __syncthreads();
   }
 }
 
 // ------------------------------------------------------------------------------------------------
 // The kernels.
 // ------------------------------------------------------------------------------------------------
-// Pack range walked by one CTA: packs first, first+stride, ... < end, U of them in flight per thread.
-//   chunk(lo, hi)  -> a dynamically claimed chunk: consecutive threads take consecutive packs
-//   grid(total)    -> static grid-stride over [0, total): used for the local (HBM-only) phases
-struct Span {
-  size_t first, end, stride;
-  static __device__ __forceinline__ Span chunk(size_t lo, size_t hi) {
-    return Span{lo + threadIdx.x, hi, static_cast<size_t>(kThreads)};
-  }
-  static __device__ __forceinline__ Span grid(size_t total) {
-    return Span{static_cast<size_t>(blockIdx.x) * kThreads + threadIdx.x, total,
-                static_cast<size_t>(gridDim.x) * kThreads};
-  }
-};
-
 template <class IN, class WIRE, class OUT>
 struct AR {
   static constexpr int kMaxSz =
@@ -406,38 +355,30 @@ struct AR {
       }
     }
   }
-  static __device__ __forceinline__ RW scale_wire(RW w, float post) {
-    if (post != 1.f) {
-      float v[P];
-      CW::to_f32(w, v);
-#pragma unroll
-      for (int k = 0; k < P; ++k) v[k] *= post;
-      w = CW::from_f32(v);
-    }
-    return w;
-  }
 
-  // ---- phase 0 (two-shot / NVLS): in -> own staging buffer (local HBM only) ----------------------
-  static __device__ __forceinline__ void stage_local(const KArgs& a, RW* dst, Span sp, float pre) {
+  // ---- phase 0 (two-shot / NVLS): in -> own staging buffer, packs [lo, hi) -----------------------
+  static __device__ __forceinline__ void stage_local(const KArgs& a, RW* dst, size_t lo, size_t hi,
+                                                     float pre) {
     const RI* in = static_cast<const RI*>(a.in);
-    const size_t full = a.count / P;  // packs that can be loaded as whole vectors
-    const size_t end = sp.end < full ? sp.end : full;
+    const size_t full = a.count / P;
+    const size_t hv = hi < full ? hi : full;
     constexpr int U = 4;
-    for (size_t i = sp.first; i < end; i += U * sp.stride) {
+    size_t i = lo + threadIdx.x;
+    for (; i + (U - 1) * kThreads < hv; i += U * kThreads) {
       RI r[U];
 #pragma unroll
-      for (int u = 0; u < U; ++u)
-        if (i + u * sp.stride < end) r[u] = __ldcs(in + i + u * sp.stride);
+      for (int u = 0; u < U; ++u) r[u] = __ldcs(in + i + u * kThreads);
 #pragma unroll
-      for (int u = 0; u < U; ++u)
-        if (i + u * sp.stride < end) dst[i + u * sp.stride] = in_to_wire(r[u], pre);
+      for (int u = 0; u < U; ++u) dst[i + u * kThreads] = in_to_wire(r[u], pre);
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0 && full < a.total_packs)
+    for (; i < hv; i += kThreads) dst[i] = in_to_wire(__ldcs(in + i), pre);
+    if (threadIdx.x == 0 && full < a.total_packs && full >= lo && full < hi)
       dst[full] = in_tail_to_wire(a, full, pre);
   }
 
   // ---- phase 0 (one-shot): in -> slot[rank] of every replica's staging buffer ---------------------
-  static __device__ __forceinline__ void stage_push(const KArgs& a, int q, Span sp, float pre) {
+  static __device__ __forceinline__ void stage_push(const KArgs& a, int q, size_t lo, size_t hi,
+                                                    float pre) {
     const RI* in = static_cast<const RI*>(a.in);
     RW* dst[kMaxWorld];
 #pragma unroll
@@ -445,23 +386,28 @@ struct AR {
       dst[p] = reinterpret_cast<RW*>(a.peer[p < a.world ? p : 0] + a.stage_off[q] +
                                      static_cast<size_t>(a.rank) * a.slot_bytes);
     const size_t full = a.count / P;
-    const size_t end = sp.end < full ? sp.end : full;
+    const size_t hv = hi < full ? hi : full;
     constexpr int U = 2;
-    for (size_t i = sp.first; i < end; i += U * sp.stride) {
+    size_t i = lo + threadIdx.x;
+    for (; i + (U - 1) * kThreads < hv; i += U * kThreads) {
       RI r[U];
 #pragma unroll
-      for (int u = 0; u < U; ++u)
-        if (i + u * sp.stride < end) r[u] = __ldcs(in + i + u * sp.stride);
+      for (int u = 0; u < U; ++u) r[u] = __ldcs(in + i + u * kThreads);
 #pragma unroll
-      for (int u = 0; u < U; ++u)
-        if (i + u * sp.stride < end) {
-          const RW w = in_to_wire(r[u], pre);
+      for (int u = 0; u < U; ++u) {
+        const RW w = in_to_wire(r[u], pre);
 #pragma unroll
-          for (int p = 0; p < kMaxWorld; ++p)
-            if (p < a.world) dst[p][i + u * sp.stride] = w;
-        }
+        for (int p = 0; p < kMaxWorld; ++p)
+          if (p < a.world) dst[p][i + u * kThreads] = w;
+      }
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0 && full < a.total_packs) {
+    for (; i < hv; i += kThreads) {
+      const RW w = in_to_wire(__ldcs(in + i), pre);
+#pragma unroll
+      for (int p = 0; p < kMaxWorld; ++p)
+        if (p < a.world) dst[p][i] = w;
+    }
+    if (threadIdx.x == 0 && full < a.total_packs && full >= lo && full < hi) {
       const RW w = in_tail_to_wire(a, full, pre);
 #pragma unroll
       for (int p = 0; p < kMaxWorld; ++p)
@@ -469,83 +415,152 @@ struct AR {
     }
   }
 
-  // ---- rank-ordered fp32 reduction from src[0..world) ----------------------------------------------
+  // ---- rank-ordered fp32 reduction of packs [lo, hi) from src[0..world) --------------------------
   // Every load of a batch is issued before the first add: world x U 16-byte requests in flight per
   // thread hide the ~2 us NVLink round trip.  `mine` (two-shot) receives the reduced wire pack in
   // place so that peers can pull it in phase 2.
   template <int MAXW, int U>
-  static __device__ __forceinline__ void reduce_packs(const KArgs& a,
-                                                      const RW* const (&src)[kMaxWorld], RW* mine,
-                                                      Span sp, float post) {
-    for (size_t i = sp.first; i < sp.end; i += U * sp.stride) {
+  static __device__ __forceinline__ void reduce_packs(const KArgs& a, const RW* const (&src)[kMaxWorld],
+                                                      RW* mine, size_t lo, size_t hi, float post) {
+    size_t i = lo + threadIdx.x;
+    for (; i + (U - 1) * kThreads < hi; i += U * kThreads) {
       RW r[U][MAXW];
 #pragma unroll
       for (int u = 0; u < U; ++u)
 #pragma unroll
         for (int p = 0; p < MAXW; ++p)
-          if (p < a.world && i + u * sp.stride < sp.end) r[u][p] = ld_sys(src[p] + i + u * sp.stride);
+          if (p < a.world) r[u][p] = ld_sys(src[p] + i + u * kThreads);
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const size_t idx = i + u * sp.stride;
-        if (idx < sp.end) {
-          float acc[P];
-          CW::to_f32(r[u][0], acc);
+        float acc[P];
+        CW::to_f32(r[u][0], acc);
 #pragma unroll
-          for (int p = 1; p < MAXW; ++p)
-            if (p < a.world) {
-              float v[P];
-              CW::to_f32(r[u][p], v);
+        for (int p = 1; p < MAXW; ++p)
+          if (p < a.world) {
+            float v[P];
+            CW::to_f32(r[u][p], v);
 #pragma unroll
-              for (int k = 0; k < P; ++k) acc[k] += v[k];
-            }
+            for (int k = 0; k < P; ++k) acc[k] += v[k];
+          }
 #pragma unroll
-          for (int k = 0; k < P; ++k) acc[k] *= post;
-          const RW w = CW::from_f32(acc);
-          if (mine) mine[idx] = w;
-          wire_to_out(a, idx, w);
-        }
+        for (int k = 0; k < P; ++k) acc[k] *= post;
+        const RW w = CW::from_f32(acc);
+        if (mine) mine[i + u * kThreads] = w;
+        wire_to_out(a, i + u * kThreads, w);
       }
+    }
+    for (; i < hi; i += kThreads) {
+      RW r[MAXW];
+#pragma unroll
+      for (int p = 0; p < MAXW; ++p)
+        if (p < a.world) r[p] = ld_sys(src[p] + i);
+      float acc[P];
+      CW::to_f32(r[0], acc);
+#pragma unroll
+      for (int p = 1; p < MAXW; ++p)
+        if (p < a.world) {
+          float v[P];
+          CW::to_f32(r[p], v);
+#pragma unroll
+          for (int k = 0; k < P; ++k) acc[k] += v[k];
+        }
+#pragma unroll
+      for (int k = 0; k < P; ++k) acc[k] *= post;
+      const RW w = CW::from_f32(acc);
+      if (mine) mine[i] = w;
+      wire_to_out(a, i, w);
     }
   }
 
   static __device__ __forceinline__ void reduce_dispatch(const KArgs& a,
                                                          const RW* const (&src)[kMaxWorld], RW* mine,
-                                                         Span sp, float post) {
+                                                         size_t lo, size_t hi, float post) {
     if (a.world <= 4)
-      reduce_packs<4, 4>(a, src, mine, sp, post);
+      reduce_packs<4, 4>(a, src, mine, lo, hi, post);
     else
-      reduce_packs<kMaxWorld, 2>(a, src, mine, sp, post);
+      reduce_packs<kMaxWorld, 2>(a, src, mine, lo, hi, post);
   }
 
-  // ---- phase 2: wire packs (a peer's reduced shard, or the local staging buffer) -> out -------------
-  static __device__ __forceinline__ void copy_out(const KArgs& a, const RW* src, Span sp) {
+  // ---- phase 2 (two-shot): pull the other replicas' reduced sub-slabs -----------------------------
+  // (peer, offset) is flattened so that every thread keeps 8 independent remote loads in flight
+  // whatever the world size.
+  static __device__ __forceinline__ void gather_packs(const KArgs& a, int q, size_t slab_lo,
+                                                      size_t M) {
+    const size_t J = static_cast<size_t>(a.world - 1) * M;
     constexpr int U = 8;
-    for (size_t i = sp.first; i < sp.end; i += U * sp.stride) {
+    auto locate = [&](size_t j, const RW*& p_src, size_t& idx) -> bool {
+      int pp = 0;
+#pragma unroll
+      for (int k = 1; k < kMaxWorld - 1; ++k) pp += (j >= k * M) ? 1 : 0;
+      const size_t off = j - pp * M;
+      int p = a.rank + 1 + pp;
+      if (p >= a.world) p -= a.world;
+      idx = slab_lo + static_cast<size_t>(p) * M + off;
+      p_src = reinterpret_cast<const RW*>(a.peer[p] + a.stage_off[q]);
+      return idx < a.total_packs;
+    };
+    size_t j = threadIdx.x;
+    for (; j + (U - 1) * kThreads < J; j += U * kThreads) {
       RW r[U];
+      size_t idx[U];
+      bool ok[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const RW* s;
+        ok[u] = locate(j + u * kThreads, s, idx[u]);
+        if (ok[u]) r[u] = ld_sys(s + idx[u]);
+      }
 #pragma unroll
       for (int u = 0; u < U; ++u)
-        if (i + u * sp.stride < sp.end) r[u] = ld_sys(src + i + u * sp.stride);
-#pragma unroll
-      for (int u = 0; u < U; ++u)
-        if (i + u * sp.stride < sp.end) wire_to_out(a, i + u * sp.stride, r[u]);
+        if (ok[u]) wire_to_out(a, idx[u], r[u]);
+    }
+    for (; j < J; j += kThreads) {
+      const RW* s;
+      size_t idx;
+      if (locate(j, s, idx)) wire_to_out(a, idx, ld_sys(s + idx));
     }
   }
 
-  // ---- NVLS phase 1: in-switch reduce of my shard, broadcast of the result -------------------------
-  static __device__ __forceinline__ void nvls_reduce(const KArgs& a, char* mc_stage, Span sp,
-                                                     float post) {
+  // ---- phase 2 (NVLS): local staging -> out over packs [lo, hi) -----------------------------------
+  static __device__ __forceinline__ void copy_out(const KArgs& a, const RW* src, size_t lo,
+                                                  size_t hi) {
+    constexpr int U = 8;
+    size_t i = lo + threadIdx.x;
+    for (; i + (U - 1) * kThreads < hi; i += U * kThreads) {
+      RW r[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) r[u] = ld_sys(src + i + u * kThreads);
+#pragma unroll
+      for (int u = 0; u < U; ++u) wire_to_out(a, i + u * kThreads, r[u]);
+    }
+    for (; i < hi; i += kThreads) wire_to_out(a, i, ld_sys(src + i));
+  }
+
+  // ---- NVLS phase 1: in-switch reduce of my sub-slab, broadcast of the result ----------------------
+  static __device__ __forceinline__ void nvls_reduce(const KArgs& a, char* mc_stage, size_t lo,
+                                                     size_t hi, float post) {
     using M = MM<WIRE, sizeof(RW)>;
     RW* mc = reinterpret_cast<RW*>(mc_stage);
     constexpr int U = 8;
-    for (size_t i = sp.first; i < sp.end; i += U * sp.stride) {
+    auto finish = [&](size_t idx, RW r) {
+      if (post != 1.f) {
+        float v[P];
+        CW::to_f32(r, v);
+#pragma unroll
+        for (int k = 0; k < P; ++k) v[k] *= post;
+        r = CW::from_f32(v);
+      }
+      M::st(mc + idx, r);
+    };
+    size_t i = lo + threadIdx.x;
+    for (; i + (U - 1) * kThreads < hi; i += U * kThreads) {
       RW r[U];
 #pragma unroll
-      for (int u = 0; u < U; ++u)
-        if (i + u * sp.stride < sp.end) r[u] = M::ld_reduce(mc + i + u * sp.stride);
+      for (int u = 0; u < U; ++u) r[u] = M::ld_reduce(mc + i + u * kThreads);
 #pragma unroll
-      for (int u = 0; u < U; ++u)
-        if (i + u * sp.stride < sp.end) M::st(mc + i + u * sp.stride, scale_wire(r[u], post));
+      for (int u = 0; u < U; ++u) finish(i + u * kThreads, r[u]);
     }
+    for (; i < hi; i += kThreads) finish(i, M::ld_reduce(mc + i));
   }
 };
 
@@ -587,110 +602,106 @@ __global__ void __launch_bounds__(kThreads) local_kernel(const __grid_constant__
     finish(full, A::in_tail_to_wire(a, full, pre));
 }
 
-// Shared prologue of the exchange kernels.
-#define TOK_EXCHANGE_PROLOGUE                                                         \
-  using A = AR<IN, WIRE, OUT>;                                                        \
-  using RW = typename A::RW;                                                          \
-  __shared__ uint32_t s_words[2];                                                     \
-  __shared__ int s_fail, s_last;                                                      \
-  __shared__ unsigned s_next;                                                         \
-  Sync st = sync_begin(a, s_words, &s_fail);                                          \
-  const int q = st.seq & 1;                                                           \
-  const float pre = (a.flags & TOK_FLAG_SCALE_POST) ? 1.f : a.scale;                  \
-  const float post = (a.flags & TOK_FLAG_SCALE_POST) ? a.scale : 1.f;                 \
-  (void)s_next;
-
-// one-shot: both phases are uniform (posted remote writes, then local reads) -> static grid-stride,
-// no atomics on the latency-critical small-bucket path.
 template <class IN, class WIRE, class OUT>
 __global__ void __launch_bounds__(kThreads, 1) one_shot_kernel(const __grid_constant__ KArgs a) {
-  TOK_EXCHANGE_PROLOGUE
+  using A = AR<IN, WIRE, OUT>;
+  __shared__ uint32_t s_words[2];
+  __shared__ int s_fail;
+  CtaState st = cta_begin(a, s_words, &s_fail);
+  const int q = st.seq & 1;
+  const float pre = (a.flags & TOK_FLAG_SCALE_POST) ? 1.f : a.scale;
+  const float post = (a.flags & TOK_FLAG_SCALE_POST) ? a.scale : 1.f;
+  const size_t lo = static_cast<size_t>(blockIdx.x) * a.packs_per_cta;
+  const size_t hi = min_sz(lo + a.packs_per_cta, a.total_packs);
+
   dbg_stamp(a, 0);
-  A::stage_push(a, q, Span::grid(a.total_packs), pre);
+  A::stage_push(a, q, lo, hi, pre);
   dbg_stamp(a, 1);
-  if (rank_barrier(a, 0, st.bar + 1, &s_last, &s_fail)) {
+  st.bar += 1;
+  if (cta_barrier(a, st.bar, &s_fail)) {
     dbg_stamp(a, 2);
-    const RW* src[kMaxWorld];
+    const typename A::RW* src[kMaxWorld];
 #pragma unroll
     for (int p = 0; p < kMaxWorld; ++p)
-      src[p] = reinterpret_cast<const RW*>(a.peer[a.rank] + a.stage_off[q] +
-                                           static_cast<size_t>(p) * a.slot_bytes);
-    A::reduce_dispatch(a, src, nullptr, Span::grid(a.total_packs), post);
+      src[p] = reinterpret_cast<const typename A::RW*>(a.peer[a.rank] + a.stage_off[q] +
+                                                       static_cast<size_t>(p) * a.slot_bytes);
+    A::reduce_dispatch(a, src, nullptr, lo, hi, post);
     dbg_stamp(a, 3);
   }
-  sync_end(a, st, 1);
+  cta_end(a, st);
 }
 
-// Shard of rank r = packs [r*Q, (r+1)*Q) with Q = shard_packs, a multiple of the chunk size C, so
-// that every chunk of the NVLink phases belongs to exactly one owner.
 template <class IN, class WIRE, class OUT>
 __global__ void __launch_bounds__(kThreads, 1) two_shot_kernel(const __grid_constant__ KArgs a) {
-  TOK_EXCHANGE_PROLOGUE
-  RW* mine = reinterpret_cast<RW*>(a.peer[a.rank] + a.stage_off[q]);
-  const size_t C = a.chunk_packs, Q = a.shard_packs;
-  const size_t shard_lo = min_sz(static_cast<size_t>(a.rank) * Q, a.total_packs);
-  const size_t shard_hi = min_sz(shard_lo + Q, a.total_packs);
+  using A = AR<IN, WIRE, OUT>;
+  __shared__ uint32_t s_words[2];
+  __shared__ int s_fail;
+  CtaState st = cta_begin(a, s_words, &s_fail);
+  const int q = st.seq & 1;
+  const float pre = (a.flags & TOK_FLAG_SCALE_POST) ? 1.f : a.scale;
+  const float post = (a.flags & TOK_FLAG_SCALE_POST) ? a.scale : 1.f;
+  const size_t lo = static_cast<size_t>(blockIdx.x) * a.packs_per_cta;
+  const size_t hi = min_sz(lo + a.packs_per_cta, a.total_packs);
+  const size_t M = a.packs_per_cta / a.world;  // sub-slab length
+  typename A::RW* mine = reinterpret_cast<typename A::RW*>(a.peer[a.rank] + a.stage_off[q]);
 
   dbg_stamp(a, 0);
-  A::stage_local(a, mine, Span::grid(a.total_packs), pre);
+  A::stage_local(a, mine, lo, hi, pre);
   dbg_stamp(a, 1);
-  bool ok = rank_barrier(a, 0, st.bar + 1, &s_last, &s_fail);
+  st.bar += 1;
+  bool ok = cta_barrier(a, st.bar, &s_fail);
   dbg_stamp(a, 2);
   if (ok) {
-    const RW* src[kMaxWorld];
+    const typename A::RW* src[kMaxWorld];
 #pragma unroll
     for (int p = 0; p < kMaxWorld; ++p)
-      src[p] = reinterpret_cast<const RW*>(a.peer[p < a.world ? p : 0] + a.stage_off[q]);
-    for_each_chunk(a, 1, (shard_hi - shard_lo + C - 1) / C, &s_next, [&](size_t c) {
-      A::reduce_dispatch(a, src, mine,
-                         Span::chunk(shard_lo + c * C, min_sz(shard_lo + (c + 1) * C, shard_hi)),
-                         post);
-    });
+      src[p] = reinterpret_cast<const typename A::RW*>(a.peer[p < a.world ? p : 0] + a.stage_off[q]);
+    const size_t slo = min_sz(lo + static_cast<size_t>(a.rank) * M, hi);
+    const size_t shi = min_sz(slo + M, hi);
+    A::reduce_dispatch(a, src, mine, slo, shi, post);
     dbg_stamp(a, 3);
-    ok = rank_barrier(a, 1, st.bar + 2, &s_last, &s_fail);
+    st.bar += 1;
+    ok = cta_barrier(a, st.bar, &s_fail);
     dbg_stamp(a, 4);
   }
-  if (ok) {
-    const size_t per_shard = Q / C;
-    for_each_chunk(a, 2, (a.total_packs + C - 1) / C, &s_next, [&](size_t c) {
-      const int owner = static_cast<int>(c / per_shard);
-      if (owner == a.rank) return;  // written to `out` while reducing
-      const RW* src = reinterpret_cast<const RW*>(a.peer[owner] + a.stage_off[q]);
-      A::copy_out(a, src, Span::chunk(c * C, min_sz((c + 1) * C, a.total_packs)));
-    });
-  }
+  if (ok) A::gather_packs(a, q, lo, M);
   dbg_stamp(a, 5);
-  sync_end(a, st, 2);
+  cta_end(a, st);
 }
 
 template <class IN, class WIRE, class OUT>
 __global__ void __launch_bounds__(kThreads, 1) nvls_kernel(const __grid_constant__ KArgs a) {
-  TOK_EXCHANGE_PROLOGUE
-  RW* mine = reinterpret_cast<RW*>(a.peer[a.rank] + a.stage_off[q]);
-  const size_t C = a.chunk_packs, Q = a.shard_packs;
-  const size_t shard_lo = min_sz(static_cast<size_t>(a.rank) * Q, a.total_packs);
-  const size_t shard_hi = min_sz(shard_lo + Q, a.total_packs);
+  using A = AR<IN, WIRE, OUT>;
+  __shared__ uint32_t s_words[2];
+  __shared__ int s_fail;
+  CtaState st = cta_begin(a, s_words, &s_fail);
+  const int q = st.seq & 1;
+  const float pre = (a.flags & TOK_FLAG_SCALE_POST) ? 1.f : a.scale;
+  const float post = (a.flags & TOK_FLAG_SCALE_POST) ? a.scale : 1.f;
+  const size_t lo = static_cast<size_t>(blockIdx.x) * a.packs_per_cta;
+  const size_t hi = min_sz(lo + a.packs_per_cta, a.total_packs);
+  const size_t M = a.packs_per_cta / a.world;
+  typename A::RW* mine = reinterpret_cast<typename A::RW*>(a.peer[a.rank] + a.stage_off[q]);
 
   dbg_stamp(a, 0);
-  A::stage_local(a, mine, Span::grid(a.total_packs), pre);
+  A::stage_local(a, mine, lo, hi, pre);
   dbg_stamp(a, 1);
-  bool ok = rank_barrier(a, 0, st.bar + 1, &s_last, &s_fail);
+  st.bar += 1;
+  bool ok = cta_barrier(a, st.bar, &s_fail);
   dbg_stamp(a, 2);
   if (ok) {
-    char* mc_stage = a.mc + a.stage_off[q];
-    for_each_chunk(a, 1, (shard_hi - shard_lo + C - 1) / C, &s_next, [&](size_t c) {
-      A::nvls_reduce(a, mc_stage,
-                     Span::chunk(shard_lo + c * C, min_sz(shard_lo + (c + 1) * C, shard_hi)), post);
-    });
+    const size_t slo = min_sz(lo + static_cast<size_t>(a.rank) * M, hi);
+    const size_t shi = min_sz(slo + M, hi);
+    A::nvls_reduce(a, a.mc + a.stage_off[q], slo, shi, post);
     dbg_stamp(a, 3);
-    ok = rank_barrier(a, 1, st.bar + 2, &s_last, &s_fail);
+    st.bar += 1;
+    ok = cta_barrier(a, st.bar, &s_fail);
     dbg_stamp(a, 4);
   }
-  if (ok) A::copy_out(a, mine, Span::grid(a.total_packs));
+  if (ok) A::copy_out(a, mine, lo, hi);
   dbg_stamp(a, 5);
-  sync_end(a, st, 2);
+  cta_end(a, st);
 }
-#undef TOK_EXCHANGE_PROLOGUE
 
 // ------------------------------------------------------------------------------------------------
 // dispatch

@@ -357,11 +357,11 @@ struct tok_comm {
   uint32_t* hostctl_dev = nullptr;
 
   // tunables
-  int max_ctas = 96;
-  size_t cta_bytes = 32768;
-  size_t chunk_packs_max = 4096;
+  int max_ctas = 64;
+  size_t cta_bytes = 65536;
   size_t one_shot_max = 256 << 10;
-  size_t nvls_min = 1 << 20;
+  bool one_shot_max_env = false;
+  size_t nvls_min = 0;
   int force_algo = 0;
   bool disable_nvls = false;
   unsigned long long barrier_timeout_ns = 20000ull * 1000000ull;
@@ -836,16 +836,12 @@ int create_impl(const char* job_id, int rank, int world, int max_world, int devi
            static_cast<uint64_t>(now_s() * 1e6);
   if (c->uid == 0) c->uid = 1;
   c->cap_bytes = round_up(env_size("TOK_STAGING_MB", 128) << 20, 2u << 20);
-  c->max_ctas = static_cast<int>(std::min<size_t>(env_size("TOK_MAX_CTAS", 96), kMaxCtas));
+  c->max_ctas = static_cast<int>(std::min<size_t>(env_size("TOK_MAX_CTAS", 64), kMaxCtas));
   if (c->max_ctas < 1) c->max_ctas = 1;
-  c->cta_bytes = std::max<size_t>(env_size("TOK_CTA_BYTES", 32768), 4096);
-  {
-    size_t cp = env_size("TOK_CHUNK_PACKS", 4096), p2 = kThreads;
-    while (p2 * 2 <= cp && p2 < 65536) p2 *= 2;  // power-of-two multiple of kThreads
-    c->chunk_packs_max = p2;
-  }
+  c->cta_bytes = std::max<size_t>(env_size("TOK_CTA_BYTES", 65536), 4096);
+  c->one_shot_max_env = getenv("TOK_ONE_SHOT_MAX") != nullptr;
   c->one_shot_max = env_size("TOK_ONE_SHOT_MAX", 256 << 10);
-  c->nvls_min = env_size("TOK_NVLS_MIN", 1 << 20);
+  c->nvls_min = env_size("TOK_NVLS_MIN", 0);
   c->force_algo = static_cast<int>(env_size("TOK_ALGO", 0));
   c->disable_nvls = env_size("TOK_DISABLE_NVLS", 0) != 0;
   c->barrier_timeout_ns = env_size("TOK_BARRIER_TIMEOUT_MS", 20000) * 1000000ull;
@@ -874,6 +870,23 @@ int create_impl(const char* job_id, int rank, int world, int max_world, int devi
   return TOK_OK;
 }
 
+// Algorithm selector.  Thresholds come from the measured sweeps on 2/4/8 B200 (profiles/): one-shot
+// moves (N-1)*S per GPU but needs a single barrier, so it wins while the bucket is latency-bound —
+// the smaller the group, the longer; NVLS wins as soon as there are >= 3 replicas and the bucket is
+// past the one-shot range; at N == 2 the in-switch reduction saves nothing and two-shot is faster.
+size_t one_shot_limit(const tok_comm* c) {
+  if (c->one_shot_max_env) return c->one_shot_max;
+  const bool mc = c->mc_va != 0;
+  switch (c->world) {
+    case 2: return 16u << 20;
+    case 3:
+    case 4: return mc ? (2u << 20) : (8u << 20);
+    case 5:
+    case 6: return mc ? (64u << 10) : (2u << 20);
+    default: return mc ? (32u << 10) : (1u << 20);
+  }
+}
+
 int pick_algo(const tok_comm* c, size_t wire_bytes) {
   if (c->world == 1) return TOK_ALGO_LOCAL;
   if (c->force_algo >= TOK_ALGO_ONE_SHOT && c->force_algo <= TOK_ALGO_NVLS) {
@@ -881,8 +894,8 @@ int pick_algo(const tok_comm* c, size_t wire_bytes) {
     return c->force_algo;
   }
   const size_t slot = c->cap_bytes / kMaxWorld;
-  if (wire_bytes <= c->one_shot_max && wire_bytes <= slot) return TOK_ALGO_ONE_SHOT;
-  if (c->mc_va && wire_bytes >= c->nvls_min) return TOK_ALGO_NVLS;
+  if (wire_bytes <= one_shot_limit(c) && wire_bytes <= slot) return TOK_ALGO_ONE_SHOT;
+  if (c->mc_va && c->world >= 3 && wire_bytes >= c->nvls_min) return TOK_ALGO_NVLS;
   return TOK_ALGO_TWO_SHOT;
 }
 
@@ -987,7 +1000,7 @@ int tok_comm_caps(tok_comm_t* c, tok_caps_t* caps) {
   caps->epoch = c->epoch;
   caps->staging_bytes = c->cap_bytes;
   caps->heap_bytes = c->heap_bytes;
-  caps->one_shot_max = c->one_shot_max;
+  caps->one_shot_max = one_shot_limit(c);
   caps->nvls_min = c->nvls_min;
   caps->max_ctas = c->max_ctas;
   caps->sm_count = c->sm_count;
@@ -1078,20 +1091,15 @@ int tok_allreduce_bucket(tok_comm_t* c, const void* in, void* out, size_t count,
     if (algo == TOK_ALGO_LOCAL) {
       const size_t want = (a.total_packs + kThreads * 4 - 1) / (kThreads * 4);
       ctas = static_cast<int>(std::min<size_t>(std::max<size_t>(want, 1), c->sm_count * 4));
-      a.chunk_packs = 0;
-      a.shard_packs = 0;
+      a.packs_per_cta = 0;
     } else {
-      // NVLink phases are cut into chunks of C packs claimed dynamically by the rank's CTAs; aim at
-      // >= 2 chunks per CTA in the shard phase, between 512 packs (one per thread) and 4096 (64 KiB).
-      const size_t per = (algo == TOK_ALGO_ONE_SHOT) ? a.total_packs
-                                                      : (a.total_packs + c->world - 1) / c->world;
-      size_t C = c->chunk_packs_max;
-      while (C > static_cast<size_t>(kThreads) && per < C * 2 * static_cast<size_t>(c->max_ctas)) C >>= 1;
-      a.chunk_packs = C;
-      a.shard_packs = round_up(per, C);
       const size_t bytes = a.total_packs * P * wsz;
-      const size_t by_bytes = (bytes + c->cta_bytes - 1) / c->cta_bytes;
-      ctas = static_cast<int>(std::min<size_t>(std::max<size_t>(by_bytes, 1), c->max_ctas));
+      size_t g = std::min<size_t>(std::max<size_t>((bytes + c->cta_bytes - 1) / c->cta_bytes, 1),
+                                  c->max_ctas);
+      size_t L = (a.total_packs + g - 1) / g;
+      if (algo != TOK_ALGO_ONE_SHOT) L = round_up(L, c->world);
+      a.packs_per_cta = L;
+      ctas = static_cast<int>((a.total_packs + L - 1) / L);
     }
     int e = launch_allreduce(algo, in_dtype, wire_dtype, out_dtype, ctas, a, cuda_stream);
     if (e != 0)

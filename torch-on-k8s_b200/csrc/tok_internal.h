@@ -10,21 +10,18 @@ namespace tok {
 
 constexpr int kMaxWorld = TOK_MAX_WORLD;
 constexpr int kThreads = 512;   // threads per CTA of every exchange kernel
-constexpr int kMaxCtas = 256;   // upper bound on the grid of an exchange kernel
+constexpr int kMaxCtas = 256;   // upper bound on the grid of an exchange kernel (flag slots)
 
 // ---- symmetric heap layout (identical offsets on every replica) -------------------------------
-//   [0, kFlagBytes)                      barrier flags   u32 flag[kMaxWorld] (one per source rank)
+//   [0, kFlagBytes)                      barrier flags   u32 flag[kMaxCtas][kMaxWorld]
 //   [kFlagBytes, +cap)                   staging buffer 0
 //   [kFlagBytes + cap, +cap)             staging buffer 1
 constexpr size_t kFlagBytes = 2u << 20;  // one 2 MiB page: keeps staging 2 MiB aligned
 
 // local (non-shared) device words, index into KArgs::ctr
-constexpr int kCtrCallSeq = 0;   // number of completed collective launches
-constexpr int kCtrBar = 1;       // number of completed cross-replica barriers
-constexpr int kCtrDone = 2;      // CTA completion ticket of the running launch
-constexpr int kCtrTicket = 4;    // [3] per-phase "CTA finished" tickets
-constexpr int kCtrWork = 8;      // [3] per-phase dynamic chunk counters
-constexpr int kCtrWords = 16;
+constexpr int kCtrCallSeq = kMaxCtas;      // number of completed collective launches
+constexpr int kCtrDone = kMaxCtas + 1;     // CTA completion ticket of the running launch
+constexpr int kCtrWords = kMaxCtas + 2;
 
 // host-mapped control words (one pinned page), index into KArgs::hostctl
 constexpr int kCtlAbort = 0;   // host -> device: leave barriers now
@@ -35,8 +32,7 @@ struct KArgs {
   void* out;
   size_t count;            // elements in this launch
   size_t total_packs;      // ceil(count / P)
-  size_t chunk_packs;      // C: packs per dynamically claimed chunk (multiple of kThreads)
-  size_t shard_packs;      // Q: packs per rank shard, multiple of C (two-shot / NVLS)
+  size_t packs_per_cta;    // slab length L (multiple of world for two-shot / NVLS)
   size_t stage_off[2];     // byte offsets of the two staging buffers inside a heap
   size_t slot_bytes;       // one-shot: stride between per-source slots inside a staging buffer
   char* peer[kMaxWorld];   // heap base of every rank as mapped in this replica (peer[rank] = own)
