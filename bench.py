@@ -285,8 +285,13 @@ def run_ours(args):
     if sizes:
         el = torch.empty(0, dtype=torch.bfloat16).element_size()
         nsets = max(2, int((160 << 20) / max(sum(sizes), 1)) + 1)
-        sets = [[torch.randn(sz // el, device=dev).to(torch.bfloat16) for sz in sizes]
-                for _ in range(min(nsets, 8))]
+        zero_copy = hook.zero_copy_buckets > 0   # same placement as DDP's own buckets
+
+        def mk(sz):
+            t = rep.comm.symm_empty(sz // el, torch.bfloat16) if zero_copy else \
+                torch.empty(sz // el, device=dev, dtype=torch.bfloat16)
+            return t.normal_()
+        sets = [[mk(sz) for sz in sizes] for _ in range(min(nsets, 8))]
         cstream = torch.cuda.Stream(device=dev)
 
         def iso_step(i):
@@ -320,6 +325,7 @@ def run_ours(args):
             iso = {"bound": "nvlink", "achieved": ach, "peak": NVLINK_PEAK_GBS, "unit": "GB/s",
                    "frac": ach / NVLINK_PEAK_GBS, "avg_launch_us": iso_ms * 1e3 / (iters * len(sizes))}
         iso["bucket_bytes"] = sizes
+        iso["zero_copy"] = bool(zero_copy)
         iso["note"] = ("the step's buckets exchanged back to back on an otherwise idle GPU, inputs "
                        "rotated over >126 MB so they are not L2 resident")
         rep.comm.status()
@@ -346,6 +352,7 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world,
                 "d2h_bytes_per_step": 4 * world, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches * world),
+        "zero_copy_buckets": bool(hook.zero_copy_buckets > 0),
         "roofline": roof,
         "roofline_isolated": iso,
     }

@@ -68,6 +68,7 @@ enum {
 #define TOK_FLAG_SCALE_POST 0x1u /* out = cast(sum(wire(in)) * scale); default is PRE:          */
                                  /* out = cast(sum(wire(in * scale))) == built-in DDP (mul by 1/N
                                     then sum)                                    */
+#define TOK_FLAG_NO_ZERO_COPY 0x2u /* always stage, even for buckets in the symmetric pool        */
 #define TOK_FLAG_ALGO_SHIFT 8    /* (TOK_ALGO_x << TOK_FLAG_ALGO_SHIFT) forces an algorithm      */
 #define TOK_FLAG_ALGO_MASK 0xF00u
 
@@ -122,6 +123,20 @@ int tok_comm_caps(tok_comm_t* comm, tok_caps_t* caps);
 int tok_allreduce_bucket(tok_comm_t* comm, const void* in, void* out, size_t count, int in_dtype,
                          int wire_dtype, int out_dtype, float scale, unsigned flags,
                          void* cuda_stream);
+
+/* Symmetric pool (zero-copy buckets).  Memory returned by tok_comm_symm_alloc lives inside this
+ * replica's heap; when EVERY replica performs the same sequence of allocations, a bucket has the
+ * same offset everywhere and tok_allreduce_bucket(in == out, one dtype) exchanges it in place —
+ * peers read it / the switch multicasts into it directly, with no staging pass (verified by an
+ * in-kernel symmetry check: TOK_ERR_STATE otherwise).  Capacity: TOK_SYMM_POOL_MB (default 1024).
+ * tok_pool_malloc/free have the torch.cuda.memory.CUDAPluggableAllocator signatures and serve the
+ * communicator selected by tok_comm_use_as_pool(), so that a torch.cuda.MemPool — and with it
+ * DistributedDataParallel's bucket storage — can live in the pool.                              */
+int tok_comm_symm_alloc(tok_comm_t* comm, size_t bytes, void** ptr);
+int tok_comm_symm_info(tok_comm_t* comm, void** base, size_t* bytes, size_t* used);
+int tok_comm_use_as_pool(tok_comm_t* comm);
+void* tok_pool_malloc(ptrdiff_t size, int device, void* cuda_stream);
+void tok_pool_free(void* ptr, size_t size, int device, void* cuda_stream);
 
 /* Which algorithm AUTO picks for `wire_bytes` on this communicator. */
 int tok_allreduce_algo(tok_comm_t* comm, size_t wire_bytes, int* algo);

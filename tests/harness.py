@@ -107,6 +107,9 @@ def run_cases(rank: int, world: int, device: int, path: str, cases: List[dict],
             pattern = case.get("pattern", "randn")
             seed = case.get("seed", 1234 + ci)
             inplace = case.get("inplace", din == dout)
+            symm = case.get("symm", False)        # bucket allocated in the symmetric pool: zero-copy
+            if symm:
+                post = True                       # the in-place kernels scale the sum
             if algo == 4 and not caps.multicast:
                 results.append(dict(case=case, skipped="no multicast"))
                 continue
@@ -115,13 +118,30 @@ def run_cases(rank: int, world: int, device: int, path: str, cases: List[dict],
             inputs = [gen_input(seed, r, count, din, pattern) for r in range(world)]
             want = allreduce_oracle(inputs, din, dw, dout, scale, post)
             with torch.cuda.stream(stream):
-                x = to_torch(inputs[rank], din, dev)
-                y = x if inplace else torch.empty(count, dtype=torch_dtype(dout), device=dev)
+                if symm:
+                    if case.get("skew") and rank == world - 1:
+                        _extra = comm.symm_empty(count, torch_dtype(din))  # steals x's block
+                    x = comm.symm_empty(count, torch_dtype(din))
+                    x.copy_(to_torch(inputs[rank], din, dev))
+                    assert comm.in_symmetric_pool(x)
+                    y = x
+                else:
+                    x = to_torch(inputs[rank], din, dev)
+                    y = x if inplace else torch.empty(count, dtype=torch_dtype(dout), device=dev)
                 t0 = time.perf_counter()
                 comm.allreduce_bucket(x, y, scale=scale, wire_dtype=torch_dtype(dw),
                                       post_scale=post, algo=algo, stream=stream)
                 stream.synchronize()
                 ms = (time.perf_counter() - t0) * 1e3
+            if case.get("skew"):
+                try:
+                    comm.status()
+                    results.append(dict(case=case, exact=False, rank=rank, ms=ms, max_ulp=-1,
+                                        mismatch=-1, note="asymmetric bucket was not detected"))
+                except Exception as e:  # noqa: BLE001
+                    results.append(dict(case=case, exact="same symmetric-pool offset" in str(e),
+                                        rank=rank, ms=ms, max_ulp=0, mismatch=0, normwise=0.0))
+                break
             comm.status()
             got = from_torch(y, dout)
             exact = bits_equal(got, want, dout)

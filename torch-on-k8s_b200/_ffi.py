@@ -29,6 +29,7 @@ TOK_F32, TOK_BF16, TOK_F16 = 0, 1, 2
 TOK_ALGO_AUTO, TOK_ALGO_LOCAL, TOK_ALGO_ONE_SHOT, TOK_ALGO_TWO_SHOT, TOK_ALGO_NVLS = 0, 1, 2, 3, 4
 ALGO_NAMES = {0: "auto", 1: "local", 2: "one_shot", 3: "two_shot", 4: "nvls"}
 TOK_FLAG_SCALE_POST = 0x1
+TOK_FLAG_NO_ZERO_COPY = 0x2
 TOK_FLAG_ALGO_SHIFT = 8
 TOK_MAX_WORLD = 8
 
@@ -88,6 +89,11 @@ PROTOTYPES = {
                                        C.c_float, C.c_uint, _P]),
     "tok_allreduce_algo": (C.c_int, [_P, C.c_size_t, _IP]),
     "tok_comm_launches": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
+    "tok_comm_symm_alloc": (C.c_int, [_P, C.c_size_t, _PP]),
+    "tok_comm_symm_info": (C.c_int, [_P, _PP, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+    "tok_comm_use_as_pool": (C.c_int, [_P]),
+    "tok_pool_malloc": (C.c_void_p, [C.c_ssize_t, C.c_int, _P]),
+    "tok_pool_free": (None, [_P, C.c_size_t, C.c_int, _P]),
     "tok_comm_debug_read": (C.c_int, [_P, C.POINTER(C.c_uint64), C.c_size_t]),
     "tok_set_feature_gates": (C.c_int, [C.c_uint]),
     "tok_get_feature_gates": (C.c_uint, []),

@@ -5,6 +5,7 @@ device memory and streams; the reduction itself is libtok8s' sm_100a kernels.
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 import os
 from typing import Optional
@@ -84,6 +85,7 @@ class Communicator:
     def allreduce_bucket(self, inp: torch.Tensor, out: Optional[torch.Tensor] = None, *,
                          scale: float = 1.0, wire_dtype: Optional[torch.dtype] = None,
                          post_scale: bool = False, algo: int = TOK_ALGO_AUTO,
+                         zero_copy: bool = True,
                          stream: Optional[torch.cuda.Stream] = None) -> torch.Tensor:
         """out = cast_out(sum over replicas of cast_wire(inp * scale)); stream-ordered, no sync."""
         if out is None:
@@ -96,13 +98,45 @@ class Communicator:
         if inp.numel() != out.numel():
             raise TokError(_ffi.TOK_ERR_INVALID, "in/out element counts differ")
         wire = wire_dtype or inp.dtype
-        flags = (TOK_FLAG_SCALE_POST if post_scale else 0) | (algo << TOK_FLAG_ALGO_SHIFT)
+        flags = (TOK_FLAG_SCALE_POST if post_scale else 0) | (algo << TOK_FLAG_ALGO_SHIFT) | \
+            (0 if zero_copy else _ffi.TOK_FLAG_NO_ZERO_COPY)
         s = stream if stream is not None else torch.cuda.current_stream(inp.device)
         check(lib().tok_allreduce_bucket(self._h, inp.data_ptr(), out.data_ptr(), inp.numel(),
                                          tok_dtype(inp.dtype), tok_dtype(wire),
                                          tok_dtype(out.dtype), float(scale), flags,
                                          C.c_void_p(s.cuda_stream)))
         return out
+
+    # ---- symmetric pool (zero-copy buckets) ---------------------------------------------------
+    def symm_info(self):
+        base, size, used = C.c_void_p(), C.c_size_t(), C.c_size_t()
+        check(lib().tok_comm_symm_info(self._h, C.byref(base), C.byref(size), C.byref(used)))
+        return base.value, size.value, used.value
+
+    def in_symmetric_pool(self, t: torch.Tensor) -> bool:
+        base, size, _ = self.symm_info()
+        return base <= t.data_ptr() and t.data_ptr() + t.numel() * t.element_size() <= base + size
+
+    def mem_pool(self) -> "torch.cuda.MemPool":
+        """A torch.cuda.MemPool whose segments are carved from this replica's symmetric pool
+        (tok_pool_malloc/free are CUDAPluggableAllocator entry points of libtok8s).  Tensors
+        allocated under `with comm.symmetric():` — in the SAME ORDER on every replica — are
+        exchanged in place by allreduce_bucket, without staging."""
+        if getattr(self, "_pool", None) is None:
+            check(lib().tok_comm_use_as_pool(self._h))
+            self._alloc = torch.cuda.memory.CUDAPluggableAllocator(_ffi.LIB_PATH, "tok_pool_malloc",
+                                                                   "tok_pool_free")
+            self._pool = torch.cuda.MemPool(self._alloc.allocator())
+        return self._pool
+
+    @contextlib.contextmanager
+    def symmetric(self):
+        with torch.cuda.use_mem_pool(self.mem_pool(), device=self.device):
+            yield
+
+    def symm_empty(self, numel: int, dtype: torch.dtype) -> torch.Tensor:
+        with self.symmetric():
+            return torch.empty(numel, dtype=dtype, device=torch.device("cuda", self.device))
 
     # ---- elastic ------------------------------------------------------------------------------
     def reform(self, new_world: int, new_rank: int, member_mask: int, epoch: int) -> None:
@@ -112,6 +146,7 @@ class Communicator:
         check(lib().tok_comm_abort(self._h))
 
     def close(self) -> None:
+        self._pool = None
         if self._h:
             lib().tok_comm_destroy(self._h)
             self._h = C.c_void_p()

@@ -227,10 +227,16 @@ TOK_MM_16BIT(__half, "f16x2")
 // per (CTA, source) suffices.  Gives up on host abort or after timeout_ns (a dead peer must not
 // hang the GPU).
 // ------------------------------------------------------------------------------------------------
+template <bool SYMCHECK = false>
 __device__ __forceinline__ bool cta_barrier(const KArgs& a, uint32_t target, int* s_fail) {
   __syncthreads();
   const int t = threadIdx.x;
   if (t < a.world) {
+    if (SYMCHECK) {  // zero-copy: tell every peer at which heap offset this replica's bucket lives
+      unsigned long long* so = reinterpret_cast<unsigned long long*>(a.peer[t] + kSymOffBytes) +
+                               (blockIdx.x * kMaxWorld + a.rank);
+      *so = static_cast<unsigned long long>(a.buf_off);
+    }
     uint32_t* remote =
         reinterpret_cast<uint32_t*>(a.peer[t]) + (blockIdx.x * kMaxWorld + a.rank);
     st_release_sys(remote, target);
@@ -253,6 +259,15 @@ __device__ __forceinline__ bool cta_barrier(const KArgs& a, uint32_t target, int
           *s_fail = 1;
           break;
         }
+      }
+    }
+    if (SYMCHECK && *s_fail == 0) {
+      const volatile unsigned long long* so =
+          reinterpret_cast<const volatile unsigned long long*>(a.peer[a.rank] + kSymOffBytes) +
+          (blockIdx.x * kMaxWorld + t);
+      if (*so != static_cast<unsigned long long>(a.buf_off)) {
+        a.hostctl[kCtlStatus] = 3;  // the replicas did not allocate this bucket symmetrically
+        *s_fail = 1;
       }
     }
   }
@@ -484,8 +499,8 @@ struct AR {
   // ---- phase 2 (two-shot): pull the other replicas' reduced sub-slabs -----------------------------
   // (peer, offset) is flattened so that every thread keeps 8 independent remote loads in flight
   // whatever the world size.
-  static __device__ __forceinline__ void gather_packs(const KArgs& a, int q, size_t slab_lo,
-                                                      size_t M) {
+  static __device__ __forceinline__ void gather_packs(const KArgs& a, size_t base_off,
+                                                      size_t slab_lo, size_t M) {
     const size_t J = static_cast<size_t>(a.world - 1) * M;
     constexpr int U = 8;
     auto locate = [&](size_t j, const RW*& p_src, size_t& idx) -> bool {
@@ -496,7 +511,7 @@ struct AR {
       int p = a.rank + 1 + pp;
       if (p >= a.world) p -= a.world;
       idx = slab_lo + static_cast<size_t>(p) * M + off;
-      p_src = reinterpret_cast<const RW*>(a.peer[p] + a.stage_off[q]);
+      p_src = reinterpret_cast<const RW*>(a.peer[p] + base_off);
       return idx < a.total_packs;
     };
     size_t j = threadIdx.x;
@@ -664,7 +679,7 @@ __global__ void __launch_bounds__(kThreads, 1) two_shot_kernel(const __grid_cons
     ok = cta_barrier(a, st.bar, &s_fail);
     dbg_stamp(a, 4);
   }
-  if (ok) A::gather_packs(a, q, lo, M);
+  if (ok) A::gather_packs(a, a.stage_off[q], lo, M);
   dbg_stamp(a, 5);
   cta_end(a, st);
 }
@@ -704,6 +719,79 @@ __global__ void __launch_bounds__(kThreads, 1) nvls_kernel(const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------------------
+// Zero-copy variants: the bucket itself lives in the symmetric pool of every replica's heap at the
+// same offset (a.buf_off), so peers read / multicast-write it directly — no staging pass, no
+// copy-out.  in == out, in dtype == wire dtype == out dtype, whole 16-byte packs; `scale` is applied
+// to the sum (== PRE for power-of-two worlds).  The first barrier also carries the symmetry check.
+// ------------------------------------------------------------------------------------------------
+template <class WIRE>
+__global__ void __launch_bounds__(kThreads, 1) nvls_inplace_kernel(const __grid_constant__ KArgs a) {
+  using A = AR<WIRE, WIRE, WIRE>;
+  __shared__ uint32_t s_words[2];
+  __shared__ int s_fail;
+  CtaState st = cta_begin(a, s_words, &s_fail);
+  const size_t lo = static_cast<size_t>(blockIdx.x) * a.packs_per_cta;
+  const size_t hi = min_sz(lo + a.packs_per_cta, a.total_packs);
+  const size_t M = a.packs_per_cta / a.world;
+  dbg_stamp(a, 0);
+  dbg_stamp(a, 1);
+  st.bar += 1;
+  bool ok = cta_barrier<true>(a, st.bar, &s_fail);
+  dbg_stamp(a, 2);
+  if (ok) {
+    const size_t slo = min_sz(lo + static_cast<size_t>(a.rank) * M, hi);
+    const size_t shi = min_sz(slo + M, hi);
+    A::nvls_reduce(a, a.mc + a.buf_off, slo, shi, a.scale);
+    dbg_stamp(a, 3);
+    st.bar += 1;
+    ok = cta_barrier(a, st.bar, &s_fail);
+    dbg_stamp(a, 4);
+  }
+  dbg_stamp(a, 5);
+  cta_end(a, st);
+}
+
+template <class WIRE>
+__global__ void __launch_bounds__(kThreads, 1)
+    two_shot_inplace_kernel(const __grid_constant__ KArgs a) {
+  using A = AR<WIRE, WIRE, WIRE>;
+  __shared__ uint32_t s_words[2];
+  __shared__ int s_fail;
+  CtaState st = cta_begin(a, s_words, &s_fail);
+  const size_t lo = static_cast<size_t>(blockIdx.x) * a.packs_per_cta;
+  const size_t hi = min_sz(lo + a.packs_per_cta, a.total_packs);
+  const size_t M = a.packs_per_cta / a.world;
+  dbg_stamp(a, 0);
+  dbg_stamp(a, 1);
+  st.bar += 1;
+  bool ok = cta_barrier<true>(a, st.bar, &s_fail);
+  dbg_stamp(a, 2);
+  if (ok) {
+    const typename A::RW* src[kMaxWorld];
+#pragma unroll
+    for (int p = 0; p < kMaxWorld; ++p)
+      src[p] = reinterpret_cast<const typename A::RW*>(a.peer[p < a.world ? p : 0] + a.buf_off);
+    const size_t slo = min_sz(lo + static_cast<size_t>(a.rank) * M, hi);
+    const size_t shi = min_sz(slo + M, hi);
+    // reduced sub-slab goes straight into a.out (== this replica's copy of the bucket)
+    A::reduce_dispatch(a, src, nullptr, slo, shi, a.scale);
+    dbg_stamp(a, 3);
+    st.bar += 1;
+    ok = cta_barrier(a, st.bar, &s_fail);
+    dbg_stamp(a, 4);
+  }
+  if (ok) {
+    A::gather_packs(a, a.buf_off, lo, M);
+    // peers may still be pulling this replica's sub-slab: nobody may return (and let the next
+    // backward overwrite the bucket) before everybody has finished reading
+    st.bar += 1;
+    cta_barrier(a, st.bar, &s_fail);
+  }
+  dbg_stamp(a, 5);
+  cta_end(a, st);
+}
+
+// ------------------------------------------------------------------------------------------------
 // dispatch
 // ------------------------------------------------------------------------------------------------
 template <class IN, class WIRE, class OUT>
@@ -721,6 +809,16 @@ int launch_typed(int algo, int ctas, const KArgs& a, cudaStream_t s) {
     case TOK_ALGO_NVLS:
       nvls_kernel<IN, WIRE, OUT><<<ctas, kThreads, 0, s>>>(a);
       break;
+    case kAlgoTwoShotInplace:
+    case kAlgoNvlsInplace:
+      if constexpr (std::is_same<IN, WIRE>::value && std::is_same<WIRE, OUT>::value) {
+        if (algo == kAlgoNvlsInplace)
+          nvls_inplace_kernel<WIRE><<<ctas, kThreads, 0, s>>>(a);
+        else
+          two_shot_inplace_kernel<WIRE><<<ctas, kThreads, 0, s>>>(a);
+        break;
+      }
+      return static_cast<int>(cudaErrorInvalidValue);
     default:
       return static_cast<int>(cudaErrorInvalidValue);
   }

@@ -340,7 +340,10 @@ struct tok_comm {
 
   size_t gran = 0;
   size_t cap_bytes = 0;
+  size_t pool_bytes = 0;   // symmetric pool for zero-copy buckets
+  size_t pool_used = 0;    // bump pointer (identical allocation sequence on every replica)
   size_t heap_bytes = 0;
+  bool zero_copy = true;
   CUmemGenericAllocationHandle local_handle = 0;
   CUdeviceptr local_va = 0;
 
@@ -369,6 +372,8 @@ struct tok_comm {
 
   std::atomic<uint64_t> launches{0};
 };
+
+static std::atomic<tok_comm*> g_pool_comm{nullptr};  // communicator behind tok_pool_malloc()
 
 namespace {
 
@@ -450,7 +455,7 @@ int alloc_local(tok_comm* c) {
   int mc = 0;
   d.cuDeviceGetAttribute_(&mc, CU_DEVICE_ATTRIBUTE_MULTICAST_SUPPORTED, c->cu_dev);
   c->mc_supported = (mc && !c->disable_nvls) ? 1 : 0;
-  size_t total = kFlagBytes + 2 * c->cap_bytes;
+  size_t total = kFlagBytes + 2 * c->cap_bytes + c->pool_bytes;
   if (c->mc_supported && c->max_world > 1) {
     CUmulticastObjectProp mp;
     memset(&mp, 0, sizeof(mp));
@@ -468,6 +473,7 @@ int alloc_local(tok_comm* c) {
       c->gran = std::max(c->gran, mg);
   }
   c->heap_bytes = round_up(total, c->gran);
+  c->pool_bytes = c->heap_bytes - kFlagBytes - 2 * c->cap_bytes;  // rounding slack joins the pool
   CU_CHECK(d.cuMemCreate_(&c->local_handle, c->heap_bytes, &prop, 0));
   int rc = map_heap(c, c->local_handle, &c->local_va);
   if (rc != TOK_OK) return rc;
@@ -836,6 +842,8 @@ int create_impl(const char* job_id, int rank, int world, int max_world, int devi
            static_cast<uint64_t>(now_s() * 1e6);
   if (c->uid == 0) c->uid = 1;
   c->cap_bytes = round_up(env_size("TOK_STAGING_MB", 128) << 20, 2u << 20);
+  c->pool_bytes = round_up(env_size("TOK_SYMM_POOL_MB", 1024) << 20, 2u << 20);
+  c->zero_copy = env_size("TOK_DISABLE_ZERO_COPY", 0) == 0;
   c->max_ctas = static_cast<int>(std::min<size_t>(env_size("TOK_MAX_CTAS", 64), kMaxCtas));
   if (c->max_ctas < 1) c->max_ctas = 1;
   c->cta_bytes = std::max<size_t>(env_size("TOK_CTA_BYTES", 65536), 4096);
@@ -957,11 +965,19 @@ int tok_comm_status(tok_comm_t* c) {
                 "a peer replica never reached the in-kernel barrier within %llu ms (rank %d of %d)",
                 c->barrier_timeout_ns / 1000000ull, c->rank, c->world);
   if (s == 2) return fail(TOK_ERR_ABORTED, "collective aborted by tok_comm_abort()");
+  if (s == 3)
+    return fail(TOK_ERR_STATE,
+                "zero-copy bucket is not at the same symmetric-pool offset on every replica (the "
+                "replicas' pool allocation sequences differ); set TOK_DISABLE_ZERO_COPY=1");
   return TOK_OK;
 }
 
 int tok_comm_destroy(tok_comm_t* c) {
   if (!c) return TOK_OK;
+  {
+    tok_comm* expect = c;
+    g_pool_comm.compare_exchange_strong(expect, nullptr);
+  }
   if (drv().ok) {
     DeviceGuard guard(c->device);
     cudaDeviceSynchronize();
@@ -1013,6 +1029,51 @@ int tok_allreduce_algo(tok_comm_t* c, size_t wire_bytes, int* algo) {
   return TOK_OK;
 }
 
+// ---- symmetric pool ---------------------------------------------------------------------------
+int tok_comm_symm_alloc(tok_comm_t* c, size_t bytes, void** ptr) {
+  if (!c || !ptr) return fail(TOK_ERR_INVALID, "comm / ptr is null");
+  const size_t need = round_up(std::max<size_t>(bytes, 1), 2u << 20);  // segment-friendly alignment
+  if (c->pool_used + need > c->pool_bytes)
+    return fail(TOK_ERR_INVALID,
+                "symmetric pool exhausted: %zu MiB used + %zu MiB requested > %zu MiB (TOK_SYMM_POOL_MB)",
+                c->pool_used >> 20, need >> 20, c->pool_bytes >> 20);
+  *ptr = reinterpret_cast<char*>(c->local_va) + kFlagBytes + 2 * c->cap_bytes + c->pool_used;
+  c->pool_used += need;
+  return TOK_OK;
+}
+
+int tok_comm_symm_info(tok_comm_t* c, void** base, size_t* bytes, size_t* used) {
+  if (!c) return fail(TOK_ERR_INVALID, "comm is null");
+  if (base) *base = reinterpret_cast<char*>(c->local_va) + kFlagBytes + 2 * c->cap_bytes;
+  if (bytes) *bytes = c->pool_bytes;
+  if (used) *used = c->pool_used;
+  return TOK_OK;
+}
+
+int tok_comm_use_as_pool(tok_comm_t* c) {
+  g_pool_comm.store(c);
+  return TOK_OK;
+}
+
+// torch.cuda.memory.CUDAPluggableAllocator entry points: segments of a torch.cuda.MemPool are carved
+// from the symmetric pool of the communicator selected with tok_comm_use_as_pool().  Freed segments
+// are not recycled (bump allocator): the pool is meant for long-lived gradient buckets.
+void* tok_pool_malloc(ptrdiff_t size, int device, void* stream) {
+  (void)stream;
+  tok_comm* c = g_pool_comm.load();
+  if (!c || size <= 0 || device != c->device) return nullptr;
+  void* p = nullptr;
+  if (tok_comm_symm_alloc(c, static_cast<size_t>(size), &p) != TOK_OK) return nullptr;
+  return p;
+}
+
+void tok_pool_free(void* ptr, size_t size, int device, void* stream) {
+  (void)ptr;
+  (void)size;
+  (void)device;
+  (void)stream;
+}
+
 int tok_comm_debug_read(tok_comm_t* c, uint64_t* out, size_t words) {
   if (!c || !out) return fail(TOK_ERR_INVALID, "comm / out is null");
   if (!c->dbg) return fail(TOK_ERR_STATE, "phase timestamps are off (set TOK_DEBUG_PHASES=1 before tok_comm_create)");
@@ -1058,11 +1119,28 @@ int tok_allreduce_bucket(tok_comm_t* c, const void* in, void* out, size_t count,
     return fail(TOK_ERR_UNSUPPORTED,
                 "NVLS requested but no multicast object is bound for this group");
 
+  // Zero-copy: the bucket lives in the symmetric pool (same offset on every replica), is exchanged
+  // in place, in its own dtype, in whole 16-byte packs -> peers read / multicast it directly.
+  const char* pool_lo = reinterpret_cast<const char*>(c->local_va) + kFlagBytes + 2 * c->cap_bytes;
+  const char* pin = static_cast<const char*>(in);
+  const bool forced = (flags & TOK_FLAG_ALGO_MASK) != 0;
+  const bool in_pool = pin >= pool_lo && pin + count * isz <= pool_lo + c->pool_bytes;
+  bool inplace = c->zero_copy && !(flags & TOK_FLAG_NO_ZERO_COPY) && c->world > 1 && in == out &&
+                 in_dtype == wire_dtype && wire_dtype == out_dtype && in_pool &&
+                 (count * wsz) % 16 == 0 && (algo == TOK_ALGO_TWO_SHOT || algo == TOK_ALGO_NVLS);
+  if (inplace && !forced && algo == TOK_ALGO_TWO_SHOT && c->mc_va && c->world >= 3)
+    algo = TOK_ALGO_NVLS;
+  size_t buf_off = 0;
+  if (inplace) {
+    buf_off = static_cast<size_t>(pin - reinterpret_cast<const char*>(c->local_va));
+    algo = (algo == TOK_ALGO_NVLS) ? kAlgoNvlsInplace : kAlgoTwoShotInplace;
+  }
+
   // largest element count one launch may take (multiple of 8 elements -> 16-byte aligned chunks)
   size_t launch_cap = c->cap_bytes / wsz;
   if (algo == TOK_ALGO_ONE_SHOT) launch_cap = (c->cap_bytes / kMaxWorld) / wsz;
   launch_cap = launch_cap / (static_cast<size_t>(P) * kMaxWorld) * (static_cast<size_t>(P) * kMaxWorld);
-  if (algo == TOK_ALGO_LOCAL) launch_cap = (static_cast<size_t>(1) << 40);
+  if (algo == TOK_ALGO_LOCAL || inplace) launch_cap = (static_cast<size_t>(1) << 40);
 
   DeviceGuard guard(c->device);
   KArgs a;
@@ -1076,6 +1154,7 @@ int tok_allreduce_bucket(tok_comm_t* c, const void* in, void* out, size_t count,
   a.hostctl = c->hostctl_dev;
   a.timeout_ns = c->barrier_timeout_ns;
   a.dbg = c->dbg;
+  a.buf_off = buf_off;
   a.scale = scale;
   a.rank = c->rank;
   a.world = c->world;
@@ -1098,6 +1177,7 @@ int tok_allreduce_bucket(tok_comm_t* c, const void* in, void* out, size_t count,
                                   c->max_ctas);
       size_t L = (a.total_packs + g - 1) / g;
       if (algo != TOK_ALGO_ONE_SHOT) L = round_up(L, c->world);
+      if (inplace) a.buf_off = buf_off + off * isz;
       a.packs_per_cta = L;
       ctas = static_cast<int>((a.total_packs + L - 1) / L);
     }

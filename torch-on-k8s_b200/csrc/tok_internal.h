@@ -14,9 +14,14 @@ constexpr int kMaxCtas = 256;   // upper bound on the grid of an exchange kernel
 
 // ---- symmetric heap layout (identical offsets on every replica) -------------------------------
 //   [0, kFlagBytes)                      barrier flags   u32 flag[kMaxCtas][kMaxWorld]
+//   [64 KiB, ...)                        u64 symoff[kMaxCtas][kMaxWorld]  zero-copy symmetry check
 //   [kFlagBytes, +cap)                   staging buffer 0
 //   [kFlagBytes + cap, +cap)             staging buffer 1
+//   [kFlagBytes + 2*cap, +pool)          symmetric pool: user buckets allocated here (identical
+//                                        allocation sequence on every replica => identical offsets)
+//                                        are exchanged in place, without staging
 constexpr size_t kFlagBytes = 2u << 20;  // one 2 MiB page: keeps staging 2 MiB aligned
+constexpr size_t kSymOffBytes = 64u << 10;  // offset of symoff[][] inside the flag page
 
 // local (non-shared) device words, index into KArgs::ctr
 constexpr int kCtrCallSeq = kMaxCtas;      // number of completed collective launches
@@ -25,7 +30,11 @@ constexpr int kCtrWords = kMaxCtas + 2;
 
 // host-mapped control words (one pinned page), index into KArgs::hostctl
 constexpr int kCtlAbort = 0;   // host -> device: leave barriers now
-constexpr int kCtlStatus = 1;  // device -> host: 0 ok, 1 timeout, 2 aborted
+constexpr int kCtlStatus = 1;  // device -> host: 0 ok, 1 timeout, 2 aborted, 3 asymmetric buffer
+
+// internal algorithm ids (zero-copy variants of the public TOK_ALGO_* ones)
+constexpr int kAlgoTwoShotInplace = 5;
+constexpr int kAlgoNvlsInplace = 6;
 
 struct KArgs {
   const void* in;
@@ -40,6 +49,7 @@ struct KArgs {
   uint32_t* ctr;           // local device words (kCtrWords)
   volatile uint32_t* hostctl;  // device pointer to the host-mapped control page
   unsigned long long timeout_ns;
+  size_t buf_off;              // zero-copy: byte offset of the bucket inside every replica's heap
   unsigned long long* dbg;     // optional [kMaxCtas][8] per-CTA phase timestamps (TOK_DEBUG_PHASES=1)
   float scale;
   int rank;

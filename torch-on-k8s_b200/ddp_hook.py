@@ -35,6 +35,7 @@ class BucketAllreduceHook:
         self.events: List[Tuple[int, torch.cuda.Event, torch.cuda.Event]] = []
         self._stream: Optional[torch.cuda.Stream] = None
         self.buckets_seen = 0
+        self.zero_copy_buckets = 0   # buckets found inside the replica's symmetric pool
 
     def _comm_stream(self, device) -> torch.cuda.Stream:
         if self._stream is None:
@@ -69,6 +70,9 @@ class BucketAllreduceHook:
             # stream and consumers synchronise their streams with it (torch.futures.Future docs).
             fut.set_result(buf)
         self.buckets_seen += 1
+        if self.buckets_seen <= 64 and self.wire_dtype in (None, buf.dtype) and \
+                self.comm.in_symmetric_pool(buf):
+            self.zero_copy_buckets += 1
         return fut
 
     def as_function(self):

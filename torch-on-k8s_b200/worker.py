@@ -29,11 +29,37 @@ class Replica:
 
     def wrap(self, model: torch.nn.Module, *, bucket_cap_mb: int = 25,
              wire_dtype: Optional[torch.dtype] = None, overlap: bool = True,
-             record_events: bool = False, **ddp_kwargs):
-        """DistributedDataParallel(model) whose gradient buckets go through libtok8s."""
+             record_events: bool = False, zero_copy: bool = True, **ddp_kwargs):
+        """DistributedDataParallel(model) whose gradient buckets go through libtok8s.
+
+        zero_copy: allocate DDP's bucket storage inside this replica's symmetric pool (a
+        torch.cuda.MemPool over libtok8s' pluggable allocator), so that with
+        gradient_as_bucket_view the gradients are produced directly in peer-mapped memory and the
+        exchange needs no staging pass.  Buckets that end up outside the pool (or a pool that cannot
+        be created) silently take the staged path — results are identical."""
         from torch.nn.parallel import DistributedDataParallel as DDP
-        ddp = DDP(model, device_ids=[self.device.index], bucket_cap_mb=bucket_cap_mb,
-                  gradient_as_bucket_view=True, **ddp_kwargs)
+        scope = None
+        if zero_copy and self.world > 1 and wire_dtype is None:
+            try:
+                self.comm.mem_pool()
+                scope = self.comm.symmetric
+            except Exception:  # noqa: BLE001 — MemPool unavailable: staged path
+                scope = None
+        if scope is None:
+            ddp = DDP(model, device_ids=[self.device.index], bucket_cap_mb=bucket_cap_mb,
+                      gradient_as_bucket_view=True, **ddp_kwargs)
+        else:
+            with scope():
+                ddp = DDP(model, device_ids=[self.device.index], bucket_cap_mb=bucket_cap_mb,
+                          gradient_as_bucket_view=True, **ddp_kwargs)
+            # DDP re-allocates its buckets once, after the first iteration, from
+            # DistributedDataParallel._pre_forward -> reducer._rebuild_buckets(): keep that in the pool
+            inner = getattr(ddp, "_pre_forward", None)
+            if inner is not None:
+                def _pre_forward(*a, **k):
+                    with scope():
+                        return inner(*a, **k)
+                ddp._pre_forward = _pre_forward
         hook = BucketAllreduceHook(self.comm, wire_dtype=wire_dtype, overlap=overlap,
                                    record_events=record_events)
         ddp.register_comm_hook(None, hook.as_function())
