@@ -53,6 +53,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--out", default="gpurun_out/sweep")
     ap.add_argument("--no-nccl", action="store_true")
+    ap.add_argument("--zero-copy", action="store_true")
     ap.add_argument("--ctas", default="")  # comma list: rebuild communicator per value
     args = ap.parse_args()
 
@@ -100,6 +101,22 @@ def main():
                     row[name + "_busbw"] = nbytes / (ms * 1e-3) * 2 * (world - 1) / world / 1e9
                     if algo == 0:
                         row["auto_algo"] = _ffi.ALGO_NAMES[comm.algo_for(nbytes)]
+                # zero-copy: the same exchange on buckets that live in the symmetric pool
+                if args.zero_copy and world > 1 and nbytes >= (1 << 16):
+                    zbufs = [comm.symm_empty(count, dt).fill_(float(rank + 1)) for _ in range(nbuf)]
+                    for algo, name in ((0, "zc_auto"), (3, "zc_two_shot")):
+                        def fnz(b, algo=algo):
+                            comm.allreduce_bucket(b, b, scale=1.0, algo=algo, stream=stream)
+                        ms = time_loop(fnz, zbufs, args.warmup, iters, stream)
+                        comm.status()
+                        row[name + "_us"] = ms * 1e3
+                        row[name + "_busbw"] = nbytes / (ms * 1e-3) * 2 * (world - 1) / world / 1e9
+                    zb = comm.symm_empty(count, dt).fill_(float(rank + 1))
+                    with torch.cuda.stream(stream):
+                        comm.allreduce_bucket(zb, zb, scale=1.0, stream=stream)
+                        stream.synchronize()
+                    row["zc_check"] = bool((zb == float(world * (world + 1) // 2)).all().item())
+                    del zbufs, zb
                 # correctness spot check: sum of rank+1 (exact in every dtype for world <= 8)
                 b = torch.full((count,), float(rank + 1), dtype=dt, device="cuda")
                 with torch.cuda.stream(stream):
