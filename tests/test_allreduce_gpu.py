@@ -51,7 +51,9 @@ def test_p2p_bit_exact_processes(tok_lib, n_gpus, world):
 def test_p2p_bit_exact_threads(tok_lib, n_gpus, world):
     devs, env = devices_for(world, n_gpus)
     env = dict(env or SHARED_ENV)
-    cases = harness.standard_cases(world, algos=(2, 3, 0), quick=True)
+    # AUTO is only bit-exact while it cannot pick NVLS (replicas sharing a GPU have no multicast)
+    algos = (2, 3, 0) if n_gpus < world else (2, 3)
+    cases = harness.standard_cases(world, algos=algos, quick=True)
     res = harness.launch(world, cases, devices=devs, mode="thread", timeout=600, env=env)
     assert_all_exact(res, len(cases), world)
 
@@ -171,6 +173,9 @@ def test_nvls_tolerance(tok_lib, n_gpus):
         for n in (9, 4097, (1 << 20) + 5):
             cases.append(dict(count=n, **{"in": a, "wire": w, "out": o}, algo=4, seed=500 + n % 97,
                               scale=1.0 / world))
+    for n in (70001, (1 << 21) + 8):   # AUTO picks NVLS for these sizes once world >= 3
+        cases.append(dict(count=n, **{"in": "bf16", "wire": "bf16", "out": "bf16"}, algo=0,
+                          seed=650 + n % 7, scale=1.0 / world))
     for dt in ("bf16", "f32"):   # zero-copy NVLS: in-switch reduce straight on the pool buckets
         for n in (4096, (1 << 20) + 64, 5 * (1 << 20)):
             cases.append(dict(count=n, **{"in": dt, "wire": dt, "out": dt}, algo=4, seed=600 + n % 89,
@@ -259,7 +264,7 @@ def test_elastic_reform_in_place(tok_lib, n_gpus):
             st = torch.cuda.Stream(device=d)
             with torch.cuda.stream(st):
                 x = harness.to_torch(ins[i], "bf16", "cuda:%d" % d)
-                comms[i].allreduce_bucket(x, x, scale=1.0 / world, stream=st)
+                comms[i].allreduce_bucket(x, x, scale=1.0 / world, stream=st, algo=3)  # exact path
                 st.synchronize()
             comms[i].status()
             outs[i] = harness.from_torch(x, "bf16")
