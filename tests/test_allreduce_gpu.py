@@ -17,7 +17,7 @@ import harness
 pytestmark = pytest.mark.gpu
 
 SHARED_ENV = {"TOK_MAX_CTAS": "16", "TOK_STAGING_MB": "32", "TOK_BARRIER_TIMEOUT_MS": "60000",
-              "TOK_SYMM_POOL_MB": "96"}
+              "TOK_SYMM_POOL_MB": "160"}
 
 
 def devices_for(world, n_gpus):
@@ -293,3 +293,103 @@ def test_elastic_reform_in_place(tok_lib, n_gpus):
     assert comms[0].caps().epoch == 2
     for c in comms.values():
         c.close()
+
+
+def test_elastic_training_without_torch_distributed(tok_lib, n_gpus):
+    """BASELINE config 2 in miniature (rescale 2 -> 4 -> 2 mid-run): ElasticDataParallel keeps its
+    gradient buckets in the symmetric pool, averages them with the zero-copy kernel, and survives
+    peer-group re-forms without restarting any process.  Every averaged bucket is checked bit-for-bit
+    against the oracle; replicas stay bit-identical; a joiner receives the parameters in place."""
+    import tempfile
+    import threading
+    import torch
+    from oracle import allreduce_oracle as O
+    from torch_on_k8s_b200.comm import Communicator
+    from torch_on_k8s_b200.elastic_dp import ElasticDataParallel
+    from workloads.mlp import batch, mlp
+    os.environ.update(SHARED_ENV)
+    path = os.path.join(tempfile.mkdtemp(prefix="tok8s-edp-"), "r")
+    devs = list(range(4)) if n_gpus >= 4 else [0] * 4
+    state, errs = {}, []
+    pre, post = {}, {}
+    init_lock = threading.Lock()   # workloads.mlp seeds the process-global CPU generator
+
+    def guarded(fn):
+        def w(i):
+            try:
+                with torch.cuda.stream(state[i]["stream"]) if i in state and "stream" in state[i] \
+                        else torch.cuda.device(devs[i]):
+                    fn(i)
+            except Exception:  # noqa: BLE001
+                import traceback
+                errs.append("%d: %s" % (i, traceback.format_exc()))
+        return w
+
+    def run_all(fn, ids):
+        ts = [threading.Thread(target=guarded(fn), args=(i,)) for i in ids]
+        [t.start() for t in ts]
+        [t.join(300) for t in ts]
+        assert not errs, errs[0]
+
+    def make(i, rank, world, epoch):
+        torch.cuda.set_device(devs[i])
+        st = torch.cuda.Stream(device=devs[i])
+        comm = Communicator("edp", rank, world, devs[i], rendezvous_path=path, max_world=4, epoch=epoch)
+        with torch.cuda.stream(st):
+            with init_lock:
+                model = mlp(seed=0 if epoch == 0 else 100 + i)   # joiners start "wrong"
+            model = model.cuda(devs[i])
+            edp = ElasticDataParallel(model, comm, algo=3)
+            x, y = batch(i, 64)
+            state[i] = dict(comm=comm, edp=edp, x=x.cuda(devs[i]), y=y.cuda(devs[i]), stream=st,
+                            opt=torch.optim.SGD(model.parameters(), lr=0.05))
+            st.synchronize()
+
+    def step(ids, tag):
+        def body(i):
+            s = state[i]
+            s["edp"].zero_grad()
+            torch.nn.functional.cross_entropy(s["edp"](s["x"]), s["y"]).backward()
+            s["stream"].synchronize()
+            pre[(tag, i)] = [b.detach().cpu().numpy().copy() for b in s["edp"].buckets]
+            s["edp"].reduce_grads(stream=s["stream"])
+            s["stream"].synchronize()
+            s["comm"].status()
+            post[(tag, i)] = [b.detach().cpu().numpy().copy() for b in s["edp"].buckets]
+            s["opt"].step()
+            s["stream"].synchronize()
+        run_all(body, ids)
+        world = len(ids)
+        for k in range(len(post[(tag, ids[0])])):
+            want = O.allreduce_oracle([pre[(tag, i)][k] for i in ids], "f32", "f32", "f32",
+                                      1.0 / world, post=True)
+            for i in ids:
+                assert np.array_equal(post[(tag, i)][k].view(np.uint32), want.view(np.uint32)), (tag, i, k)
+        flat = {i: torch.cat([p.detach().flatten() for p in state[i]["edp"].module.parameters()]).cpu()
+                for i in ids}
+        for i in ids[1:]:
+            assert torch.equal(flat[ids[0]], flat[i]), (tag, i)   # replicas stay bit-identical
+
+    run_all(lambda i: make(i, i, 2, 0), [0, 1])
+    assert len(state[0]["edp"].buckets) >= 1 and state[0]["comm"].in_symmetric_pool(state[0]["edp"].buckets[0])
+    step([0, 1], "w2a")
+    step([0, 1], "w2b")
+
+    def grow(i):
+        if i < 2:
+            state[i]["edp"].reform(4, i, 0b11, 1)
+        else:
+            make(i, i, 4, 1)
+    run_all(grow, [0, 1, 2, 3])
+    run_all(lambda i: (state[i]["edp"].sync_params(root=0), state[i]["stream"].synchronize()), [0, 1, 2, 3])
+    step([0, 1, 2, 3], "w4a")
+    step([0, 1, 2, 3], "w4b")
+
+    keep = [0, 2]
+    for i in (1, 3):
+        state.pop(i)["comm"].close()
+    run_all(lambda i: state[i]["edp"].reform(2, keep.index(i), 0b0101, 2), keep)
+    step(keep, "w2c")
+    assert state[0]["comm"].caps().epoch == 2
+    for s in state.values():
+        s["comm"].close()
