@@ -361,6 +361,7 @@ struct tok_comm {
 
   // tunables
   int max_ctas = 64;
+  int zc_ctas = 0;          // 0 = built-in rule for the zero-copy kernels
   size_t cta_bytes = 65536;
   size_t one_shot_max = 256 << 10;
   bool one_shot_max_env = false;
@@ -846,6 +847,7 @@ int create_impl(const char* job_id, int rank, int world, int max_world, int devi
   c->zero_copy = env_size("TOK_DISABLE_ZERO_COPY", 0) == 0;
   c->max_ctas = static_cast<int>(std::min<size_t>(env_size("TOK_MAX_CTAS", 64), kMaxCtas));
   if (c->max_ctas < 1) c->max_ctas = 1;
+  c->zc_ctas = static_cast<int>(std::min<size_t>(env_size("TOK_ZC_CTAS", getenv("TOK_MAX_CTAS") ? c->max_ctas : 0), kMaxCtas));
   c->cta_bytes = std::max<size_t>(env_size("TOK_CTA_BYTES", 65536), 4096);
   c->one_shot_max_env = getenv("TOK_ONE_SHOT_MAX") != nullptr;
   c->one_shot_max = env_size("TOK_ONE_SHOT_MAX", 256 << 10);
@@ -1176,8 +1178,15 @@ int tok_allreduce_bucket(tok_comm_t* c, const void* in, void* out, size_t count,
       a.packs_per_cta = 0;
     } else {
       const size_t bytes = a.total_packs * P * wsz;
+      size_t cap_ctas = c->max_ctas;
+      if (inplace) {
+        // in-place NVLS saturates the switch with few requesters: measured on 4xB200, 32 CTAs beat
+        // 64/96/128 from 16 MiB up (94 vs 103-114 us at 32 MiB), 64 win below
+        cap_ctas = c->zc_ctas ? c->zc_ctas
+                              : ((algo == kAlgoNvlsInplace && bytes >= (12u << 20)) ? 32 : 64);
+      }
       size_t g = std::min<size_t>(std::max<size_t>((bytes + c->cta_bytes - 1) / c->cta_bytes, 1),
-                                  c->max_ctas);
+                                  cap_ctas);
       size_t L = (a.total_packs + g - 1) / g;
       if (algo != TOK_ALGO_ONE_SHOT) L = round_up(L, c->world);
       if (inplace) a.buf_off = buf_off + off * isz;
