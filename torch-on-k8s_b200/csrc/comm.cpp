@@ -1180,10 +1180,18 @@ int tok_allreduce_bucket(tok_comm_t* c, const void* in, void* out, size_t count,
       const size_t bytes = a.total_packs * P * wsz;
       size_t cap_ctas = c->max_ctas;
       if (inplace) {
-        // in-place NVLS saturates the switch with few requesters: measured on 4xB200, 32 CTAs beat
-        // 64/96/128 from 16 MiB up (94 vs 103-114 us at 32 MiB), 64 win below
-        cap_ctas = c->zc_ctas ? c->zc_ctas
-                              : ((algo == kAlgoNvlsInplace && bytes >= (12u << 20)) ? 32 : 64);
+        // in-place NVLS saturates the NVSwitch reduction path with few requesters — more CTAs only
+        // add contention (measured, profiles/r01_sweep_n{4,8}_zero_copy_cta_tuning.json: at N=8
+        // 32 MiB takes 91 us with 16 CTAs, 99 with 32, 112 with 64; below ~12 MiB 64 CTAs win).
+        // Fewer CTAs also leave the SMs to the backward pass the exchange overlaps with.
+        if (c->zc_ctas)
+          cap_ctas = c->zc_ctas;
+        else if (algo == kAlgoNvlsInplace && bytes >= (24u << 20))
+          cap_ctas = 16;
+        else if (algo == kAlgoNvlsInplace && bytes >= (12u << 20))
+          cap_ctas = 32;
+        else
+          cap_ctas = 64;
       }
       size_t g = std::min<size_t>(std::max<size_t>((bytes + c->cta_bytes - 1) / c->cta_bytes, 1),
                                   cap_ctas);
