@@ -1180,16 +1180,15 @@ int tok_allreduce_bucket(tok_comm_t* c, const void* in, void* out, size_t count,
       const size_t bytes = a.total_packs * P * wsz;
       size_t cap_ctas = c->max_ctas;
       if (inplace) {
-        // in-place NVLS saturates the NVSwitch reduction path with few requesters — more CTAs only
-        // add contention (measured, profiles/r01_sweep_n{4,8}_zero_copy_cta_tuning.json: at N=8
-        // 32 MiB takes 91 us with 16 CTAs, 99 with 32, 112 with 64; below ~12 MiB 64 CTAs win).
-        // Fewer CTAs also leave the SMs to the backward pass the exchange overlaps with.
+        // In-place NVLS saturates the NVSwitch reduction path with few requesters: in the isolated
+        // sweeps (profiles/r01_sweep_n{4,8}_zero_copy_cta_tuning.json) 16 CTAs beat 64 from 32 MiB
+        // up at N=8 (91 vs 112 us at 32 MiB, 160 vs 184 at 64 MiB).  Below that the evidence is
+        // within run-to-run noise, and the ResNet-50 buckets (22.9 / 28.3 MB) measured best with 64
+        // CTAs inside bench.py (77 us/bucket vs 87 with 16-32 CTAs), so 64 stays the default there.
         if (c->zc_ctas)
           cap_ctas = c->zc_ctas;
-        else if (algo == kAlgoNvlsInplace && bytes >= (24u << 20))
+        else if (algo == kAlgoNvlsInplace && bytes >= (32u << 20))
           cap_ctas = 16;
-        else if (algo == kAlgoNvlsInplace && bytes >= (12u << 20))
-          cap_ctas = 32;
         else
           cap_ctas = 64;
       }
