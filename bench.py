@@ -342,8 +342,9 @@ def run_ours(args):
         "warmup": W, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": "ResNet-50 bf16 synthetic 224x224 images (random-init weights), "
-                               "per-GPU batch %d, DDP bucket 25MB (3 buckets: 4.1/28.9/18.1 MB = "
-                               "51.1 MB/step/replica), SGD momentum, channels_last" % B,
+                               "per-GPU batch %d, DDP bucket 25MB (4.1/28.9/18.1 MB at iteration 0, "
+                               "rebuilt by DDP into 28.3/22.9 MB; 51.1 MB/step/replica), SGD "
+                               "momentum, channels_last" % B,
                    "global_batch": B * world, "parallelism": "dp%d" % world,
                    "l2": "step working set (GBs of activations) is larger than the 126 MB L2; "
                          "no explicit flush",

@@ -2,7 +2,6 @@
 reference (oracle/controlplane_oracle.py) and against hand-derived known answers from SURVEY.md
 Appendix A.  CPU only — the reference ships no tests (parity unpinned by the reference)."""
 import copy
-import itertools
 import json
 import random
 

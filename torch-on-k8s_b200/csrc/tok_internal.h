@@ -57,12 +57,6 @@ struct KArgs {
   uint32_t flags;          // TOK_FLAG_SCALE_POST
 };
 
-struct LaunchPlan {
-  int algo;      // TOK_ALGO_*
-  int ctas;
-  int pack;      // elements per pack
-};
-
 // Implemented in allreduce.cu.  Returns cudaError_t as int (0 = success).
 int launch_allreduce(int algo, int in_dtype, int wire_dtype, int out_dtype, int ctas,
                      const KArgs& args, void* stream);

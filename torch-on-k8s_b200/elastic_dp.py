@@ -21,7 +21,6 @@ from typing import List, Optional
 
 import torch
 
-from . import _ffi
 from ._ffi import check, lib
 from .comm import Communicator
 

@@ -7,7 +7,6 @@ import ctypes as C
 import json
 from typing import Dict, List, Optional, Union
 
-from . import _ffi
 from ._ffi import call_json, check, lib
 
 TASK_ORDER = ["AIMaster", "Master", "Worker"]  # GetTaskReconcilerOrders, torchjob_controller.go:464-471
