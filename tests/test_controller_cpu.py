@@ -57,6 +57,11 @@ def test_mlp_torchjob_world2_matches_golden(tok_lib, tmp_path, monkeypatch):
     st = ctl.jobs[uid].job.status
     assert st["taskStatuses"]["Master"]["succeed"] == 1 and st["taskStatuses"]["Worker"]["succeed"] == 1
     assert len(ctl.free_gpus) == 2
+    text = ctl.metrics.render()      # the reference's metric names (pkg/metrics/metrics.go)
+    assert 'torch_on_k8s_jobs_created_total{kind="TorchJob"} 1.0' in text
+    assert 'torch_on_k8s_jobs_successful_total{kind="TorchJob"} 1.0' in text
+    assert "torch_on_k8s_jobs_all_pods_launch_delay_seconds_count" in text
+    assert 'torch_on_k8s_tenant_queue_jobs_pending_count{queue="default"} 0.0' in text
 
 
 def test_two_queued_jobs_gang_on_two_slots(tok_lib, tmp_path, monkeypatch):

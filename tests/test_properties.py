@@ -1,0 +1,115 @@
+"""Property / fuzz tests of the host logic behind the C ABI (CPU only)."""
+import json
+import math
+
+import pytest
+from hypothesis import given, settings
+from hypothesis import strategies as st
+
+from oracle import controlplane_oracle as O
+from torch_on_k8s_b200 import _ffi
+from torch_on_k8s_b200.coordinator import Coordinator
+from torch_on_k8s_b200.job import TorchJob
+from torch_on_k8s_b200.sampler import ReplicaSampler
+
+json_scalars = st.one_of(st.none(), st.booleans(), st.integers(-2**53, 2**53),
+                         st.floats(allow_nan=False, allow_infinity=False, width=64),
+                         st.text(max_size=20))
+json_values = st.recursive(json_scalars,
+                           lambda c: st.one_of(st.lists(c, max_size=4),
+                                               st.dictionaries(st.text(max_size=8), c, max_size=4)),
+                           max_leaves=20)
+
+
+@settings(max_examples=150, deadline=None)
+@given(extra=json_values, labels=st.dictionaries(st.text(max_size=10), st.text(max_size=10), max_size=4))
+def test_manifest_round_trip_preserves_unknown_fields(tok_lib, extra, labels):
+    """The C++ JSON model (csrc/json.cpp) must round-trip whatever a PodTemplateSpec may carry:
+    unicode, escapes, big integers, floats, nesting."""
+    m = {"metadata": {"name": "j", "labels": labels},
+         "spec": {"torchTaskSpecs": {"Master": {"template": {"spec": {"containers": [
+             {"name": "torch", "x-extra": extra}]}}}}}}
+    d = TorchJob(json.dumps(m), apply_defaults=False).to_dict()
+    assert d["metadata"]["labels"] == labels
+    got = d["spec"]["torchTaskSpecs"]["Master"]["template"]["spec"]["containers"][0]["x-extra"]
+    assert got == extra or (isinstance(extra, float) and math.isclose(got, extra, rel_tol=0, abs_tol=0))
+
+
+@settings(max_examples=80, deadline=None)
+@given(text=st.text(max_size=60))
+def test_parser_never_crashes_on_garbage(tok_lib, text):
+    try:
+        TorchJob(text, apply_defaults=False)
+    except _ffi.TokError as e:
+        assert e.code == _ffi.TOK_ERR_INVALID
+
+
+@settings(max_examples=60, deadline=None)
+@given(weights=st.lists(st.integers(1, 7), min_size=1, max_size=5))
+def test_wrr_is_proportional_over_a_cycle(tok_lib, weights):
+    """Over sum(w)/gcd(w) consecutive picks every queue is selected exactly w_i/gcd times
+    (pkg/coordinator/core/policy.go:203-221); C ABI and oracle agree pick for pick."""
+    c = Coordinator(policy="wrr", weight_mode="replicas")
+    c.set_quota("", 0)                       # nothing can dequeue: weights stay constant
+    o = O.WeightedRoundRobin()
+    for i, w in enumerate(weights):          # a job with (w-1) workers + 1 master has w replicas
+        m = {"metadata": {"name": "j%d" % i}, "spec": {"schedulingPolicy": {"queue": "q%d" % i},
+             "torchTaskSpecs": {"Master": {}, **({"Worker": {"numTasks": w - 1}} if w > 1 else {})}}}
+        c.enqueue(TorchJob(m), "u%d" % i)
+    g = 0
+    for w in weights:
+        g = math.gcd(g, w)
+    cycle = sum(weights) // g
+    names = ["q%d" % i for i in range(len(weights))]
+    picks = [c.tick(float(k))["queue"] for k in range(2 * cycle)]
+    want = [o.next(list(zip(names, weights))) for _ in range(2 * cycle)]
+    assert picks == want
+    for i, w in enumerate(weights):
+        assert picks[:cycle].count(names[i]) == w // g
+        assert picks[cycle:].count(names[i]) == w // g
+
+
+@settings(max_examples=100, deadline=None)
+@given(n=st.integers(1, 200), world=st.integers(1, 8), epoch=st.integers(0, 5), seed=st.integers(0, 99),
+       drop_last=st.booleans())
+def test_sampler_shards_partition_the_permutation(n, world, epoch, seed, drop_last):
+    shards = []
+    for r in range(world):
+        s = ReplicaSampler(n, world, r, seed=seed, drop_last=drop_last)
+        s.set_epoch(epoch)
+        shards.append(list(s))
+        assert len(shards[-1]) == len(s)
+    assert len({len(x) for x in shards}) == 1           # every replica sees the same number of samples
+    flat = [i for x in shards for i in x]
+    if drop_last and n % world:
+        assert len(set(flat)) == len(flat) and set(flat) <= set(range(n))
+    else:
+        assert set(flat) == set(range(n))                # padding repeats, never drops
+    # and it is exactly the oracle's restatement of DistributedSampler's arithmetic
+    import torch
+    g = torch.Generator()
+    g.manual_seed(seed + epoch)
+    perm = torch.randperm(n, generator=g).tolist()
+    for r in range(world):
+        assert shards[r] == O_shard(perm, r, world, drop_last)
+
+
+def O_shard(perm, rank, world, drop_last):
+    from oracle.allreduce_oracle import shard_indices
+    if drop_last and len(perm) % world and len(perm) < world:
+        return []
+    return shard_indices(perm, rank, world, drop_last)
+
+
+def test_oracle_env_equals_c_abi_env(tok_lib):
+    """oracle/gloo_torchjob.replica_env (what the CPU baseline is wired with) == tok_job_cluster_spec."""
+    from oracle.gloo_torchjob import replica_env
+    for workers in range(0, 8):
+        m = {"metadata": {"name": "bench-ref"}, "spec": {"torchTaskSpecs": {
+            "Master": {"template": {"spec": {"containers": [{"name": "torch"}]}}},
+            **({"Worker": {"numTasks": workers, "template": {"spec": {"containers": [{"name": "torch"}]}}}}
+               if workers else {})}}}
+        j = TorchJob(m)
+        assert j.replica_env("master", 0) == replica_env("bench-ref", "master", 0, workers)
+        for i in range(workers):
+            assert j.replica_env("worker", i) == replica_env("bench-ref", "worker", i, workers)

@@ -33,6 +33,7 @@ from typing import Dict, List, Optional
 
 from .coordinator import SCHEDULING_PERIOD_S, Coordinator
 from .job import TASK_ORDER, TorchJob, should_failover
+from .metrics import KIND, Metrics
 
 
 def _now() -> str:
@@ -74,6 +75,8 @@ class Controller:
         self.log_dir = log_dir
         self.rdzv_dir = rdzv_dir
         self.events: List[tuple] = []
+        self.metrics = Metrics()
+        self._t_created: Dict[str, float] = {}
 
     # ---- submit (owner create) -------------------------------------------------------------------
     def submit(self, manifest, command: Optional[List[str]] = None) -> str:
@@ -89,6 +92,8 @@ class Controller:
             job.set_condition("Queuing", "JobEnqueued",
                               "Job %s is queuing and waiting for being scheduled." % uid, _now())
         self._event(uid, "JobEnqueued")
+        self.metrics.created.labels(KIND).inc()
+        self._t_created[uid] = time.time()
         return uid
 
     def _event(self, uid, reason, msg=""):
@@ -111,6 +116,11 @@ class Controller:
         for mj in list(self.jobs.values()):
             if mj.dequeued and not mj.done:
                 self._reconcile(mj)
+        states = [m.job.last_condition() for m in self.jobs.values() if not m.done]
+        self.metrics.running.labels(KIND).set(sum(s in ("Running", "Restarting") for s in states))
+        self.metrics.pending.labels(KIND).set(sum(s in ("Created", "Queuing") for s in states))
+        for tenant in {self._tenant(m) for m in self.jobs.values()}:
+            self.metrics.queue_pending.labels(tenant).set(self.coord.pending(tenant))
 
     @staticmethod
     def _tenant(mj: ManagedJob) -> str:
@@ -180,6 +190,13 @@ class Controller:
         mj.replicas[tt][idx] = ReplicaProc(tt, idx, gpu, proc, "Running", restarts=restarts,
                                            log_path=log.name if log else None)
         self._event(mj.uid, "SuccessfulCreatePod", spec["name"])
+        d = mj.job.to_dict()["metadata"]
+        lbl = (KIND, d["name"], d.get("namespace", "default"), mj.uid)
+        created = sum(len(v) for v in mj.replicas.values())
+        if created == 1 and restarts == 0:
+            self.metrics.first_pod_delay.labels(*lbl).observe(time.time() - self._t_created.get(mj.uid, time.time()))
+        if created == mj.job.world_size + mj.job.num_tasks("AIMaster") and restarts == 0:
+            self.metrics.all_pods_delay.labels(*lbl).observe(time.time() - self._t_created.get(mj.uid, time.time()))
 
     def _container_command(self, mj: ManagedJob, tt: str) -> List[str]:
         c = None
@@ -211,6 +228,7 @@ class Controller:
                 if code != 0 and should_failover(policy, code, ""):
                     del reps[idx]              # recreated next pass with the same index => same RANK
                     restarting = True
+                    self.metrics.restarted.labels(KIND).inc()
                     self._event(mj.uid, "FailoverRecreate", "%s-%d" % (tt, idx))
                 elif code != 0 and policy in ("OnFailure", "Always"):
                     limit = (mj.job.to_dict()["spec"].get("backoffLimit"))
@@ -240,6 +258,8 @@ class Controller:
                     self._release(mj, r)
         mj.done = True
         self._event(mj.uid, "Job" + (mj.job.last_condition() or ""))
+        (self.metrics.successful if mj.job.last_condition() == "Succeeded" else self.metrics.failed) \
+            .labels(KIND).inc()
 
     # ---- helpers ------------------------------------------------------------------------------------------
     def run_until_done(self, timeout: float = 600.0, period: float = SCHEDULING_PERIOD_S) -> Dict[str, str]:
