@@ -263,6 +263,10 @@ def run_ours(args):
                 "kernel": "tok::local_kernel<bf16,bf16,bf16>",
                 "algorithmic_bytes_per_launch": 2.0 * bucket_bytes / n_launch,
                 "avg_launch_us": ar_ms_max * 1e3 / n_launch, "peak_source": peak_kind + " hbm_gbs",
+                "traffic_note": "ncu --set full of the same kernel at 2x512 MiB: dram read+write "
+                                "1015 MB per launch vs 1074 MB algorithmic, 6.04 TB/s "
+                                "(profiles/r01_ncu_local_kernel_raw.csv); not captured at the "
+                                "bucket sizes of this run, hence traffic=null",
                 "note": "world=1 degenerates to the fused scale/cast copy: bytes = S_in + S_out"}
     else:
         algbw = wire_bytes / (ar_ms_max * 1e-3) / 1e9 if ar_ms_max > 0 else 0.0

@@ -113,3 +113,32 @@ def test_oracle_env_equals_c_abi_env(tok_lib):
         assert j.replica_env("master", 0) == replica_env("bench-ref", "master", 0, workers)
         for i in range(workers):
             assert j.replica_env("worker", i) == replica_env("bench-ref", "worker", i, workers)
+
+
+def test_bucket_assignment_matches_torch_reducer():
+    """ElasticDataParallel's bucket assignment == torch's Reducer
+    (compute_bucket_assignment_by_size), incl. the BASELINE bucket sizes of SURVEY §8a."""
+    import torch
+    import torch.distributed as dist
+    from torch_on_k8s_b200.elastic_dp import bucket_assignment
+    from workloads.mlp import mlp
+    from workloads.resnet50 import resnet50
+
+    def check(params, caps):
+        want, _ = dist._compute_bucket_assignment_by_size(params, caps)
+        got = bucket_assignment([p.numel() * p.element_size() for p in params],
+                                [(p.dtype, p.device) for p in params], caps)
+        assert got == want
+        return [sum(params[i].numel() * params[i].element_size() for i in b) for b in got]
+
+    caps = [1 << 20, 25 << 20]
+    rn = [p for p in resnet50().to(torch.bfloat16).parameters()][::-1]
+    assert check(rn, caps) == [4098000, 28878848, 18137216]          # SURVEY §8a, bf16
+    rn32 = [p for p in resnet50().parameters()][::-1]
+    assert check(rn32, caps) == [8196000, 31502336, 26255360, 26550272, 9724160]   # fp32
+    assert check([p for p in mlp().parameters()][::-1], caps) == [407080]
+    mixed = [torch.nn.Parameter(torch.zeros(n, dtype=dt)) for n, dt in
+             [(300000, torch.float32), (10, torch.bfloat16), (700000, torch.float32),
+              (2 << 20, torch.bfloat16), (5, torch.float32), (9 << 20, torch.float32)]]
+    check(mixed, caps)
+    check(mixed, [1 << 20])

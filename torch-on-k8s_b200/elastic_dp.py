@@ -42,6 +42,30 @@ def symm_tensor(comm: Communicator, numel: int, dtype: torch.dtype) -> torch.Ten
     return raw[:nbytes].view(dtype)
 
 
+def bucket_assignment(sizes_bytes, keys, caps):
+    """Gradient-bucket assignment of torch's Reducer (compute_bucket_assignment_by_size, reached from
+    torch/nn/parallel/distributed.py:1183-1275 — SURVEY.md §8 row a10): walk the tensors in the given
+    order, one open bucket per (dtype, device) key; a bucket is closed as soon as its size REACHES
+    its limit; the limits advance through `caps` per key ([first 1 MiB, then bucket_cap]); buckets
+    are returned ordered by their smallest tensor index.  Pure function (unit-tested on CPU against
+    torch.distributed._compute_bucket_assignment_by_size)."""
+    open_b, cap_pos, out = {}, {}, []
+    for i, (nb, k) in enumerate(zip(sizes_bytes, keys)):
+        idx, size = open_b.get(k, ([], 0))
+        idx = idx + [i]
+        size += nb
+        pos = cap_pos.get(k, 0)
+        if size >= caps[pos]:
+            out.append(idx)
+            open_b[k] = ([], 0)
+            cap_pos[k] = min(pos + 1, len(caps) - 1)
+        else:
+            open_b[k] = (idx, size)
+    out += [idx for idx, _ in open_b.values() if idx]
+    out.sort(key=min)
+    return out
+
+
 class ElasticDataParallel(torch.nn.Module):
     def __init__(self, module: torch.nn.Module, comm: Communicator, *, bucket_cap_mb: int = 25,
                  first_bucket_mb: int = 1, algo: int = 0):
@@ -54,24 +78,16 @@ class ElasticDataParallel(torch.nn.Module):
 
     def _assign(self, cap: int, first_cap: int) -> None:
         params = [p for p in self.module.parameters() if p.requires_grad][::-1]  # reverse order
-        groups, cur, cur_bytes, limit = [], [], 0, first_cap
-        for p in params:
-            nb = p.numel() * p.element_size()
-            if cur and (cur_bytes + nb > limit or p.dtype != cur[0].dtype):
-                groups.append(cur)
-                cur, cur_bytes, limit = [], 0, cap
-            cur.append(p)
-            cur_bytes += nb
-        if cur:
-            groups.append(cur)
+        groups = bucket_assignment([p.numel() * p.element_size() for p in params],
+                                   [(p.dtype, p.device) for p in params], [first_cap, cap])
         for g in groups:
-            total = sum((p.numel() + 7) // 8 * 8 for p in g)     # keep every view 16-byte aligned
-            flat = symm_tensor(self.comm, total, g[0].dtype)
+            ps = [params[i] for i in g]
+            total = sum((p.numel() + 7) // 8 * 8 for p in ps)    # keep every view 16-byte aligned
+            flat = symm_tensor(self.comm, total, ps[0].dtype)
             flat.zero_()
             off = 0
-            for p in g:
-                view = flat[off:off + p.numel()].view(p.shape)
-                p.grad = view
+            for p in ps:
+                p.grad = flat[off:off + p.numel()].view(p.shape)
                 off += (p.numel() + 7) // 8 * 8
             self.buckets.append(flat)
 
