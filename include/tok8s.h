@@ -198,6 +198,16 @@ int tok_failover_decide(const char* restart_policy, int exit_code, const char* r
 int tok_job_update_status(tok_job_t* job, const char* replicas_json, int restarting,
                           const char* now_rfc3339, char** status_json);
 
+/* Termination policies of ReconcileJobs (controllers/common/job.go:100-200): backoffLimit
+ * (exceedsBackoffLimit / pastBackoffLimit :385-419), activeDurations (:422-430), cleanPodPolicy
+ * (:433-460), TTLSecondsAfterFinished (:511-539).  replicas_json: {"Worker":[{"phase","restartCount"}]};
+ * prev_retries = requeues so far.  Updates job.status (Failed condition, completionTime, folding of
+ * active into succeed on success) and returns JSON {"terminate","exceedsBackoffLimit",
+ * "pastBackoffLimit","pastActiveDeadline","deletePods":"None|Running|All","deleteJob","requeueAfter",
+ * "message","status"}.                                                                            */
+int tok_job_check_termination(tok_job_t* job, const char* replicas_json, int prev_retries,
+                              const char* now_rfc3339, char** json);
+
 /* setCondition / filterOutCondition (pkg/utils/utils.go:186-243): append `type` (status True) unless
  * the job is already Failed/Succeeded or the (status, reason) is unchanged; Running <-> Restarting
  * evict each other; Failed/Succeeded flip Running to False.                                      */

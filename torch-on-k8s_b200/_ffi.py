@@ -106,6 +106,7 @@ PROTOTYPES = {
     "tok_gang_admit": (C.c_int, [_P, C.c_int, _SP]),
     "tok_failover_decide": (C.c_int, [_S, C.c_int, _S, _IP]),
     "tok_job_update_status": (C.c_int, [_P, _S, C.c_int, _S, _SP]),
+    "tok_job_check_termination": (C.c_int, [_P, _S, C.c_int, _S, _SP]),
     "tok_job_set_condition": (C.c_int, [_P, _S, _S, _S, _S]),
     "tok_job_need_enqueue": (C.c_int, [_P, _IP]),
     "tok_coord_create": (C.c_int, [C.c_int, C.c_int, C.c_uint64, _PP]),

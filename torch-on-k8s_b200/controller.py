@@ -62,6 +62,7 @@ class ManagedJob:
     dequeued: bool = False
     gpus: List[int] = field(default_factory=list)
     done: bool = False
+    retries: int = 0          # BackoffStatesQueue.NumRequeues stand-in (failover passes so far)
 
 
 class Controller:
@@ -138,6 +139,18 @@ class Controller:
             mj.admitted = True
             self._event(mj.uid, "GangAdmitted", "slots=%d" % g["slotsNeeded"])
         restarting = self._poll(mj)
+        if restarting:
+            mj.retries += 1
+        # termination policies first, as ReconcileJobs does (controllers/common/job.go:100-200)
+        pods = {tt: [dict(phase=r.phase, restartCount=r.restarts) for r in v.values()]
+                for tt, v in mj.replicas.items()}
+        term = job.check_termination(pods, mj.retries, _now())
+        if term["terminate"]:
+            if term.get("message"):
+                self._event(mj.uid, "JobFailed", term["message"])
+            self.coord.job_settled(mj.uid)
+            self._finish(mj, term.get("deletePods", "None"))
+            return
         specs = job.task_specs
         for tt in TASK_ORDER + [k for k in specs if k not in TASK_ORDER]:
             if tt not in specs:
@@ -157,7 +170,8 @@ class Controller:
         if last in ("Running", "Failed", "Succeeded"):
             self.coord.job_settled(mj.uid)
         if last in ("Failed", "Succeeded"):
-            self._finish(mj)
+            term = job.check_termination(pods, mj.retries, _now())
+            self._finish(mj, term.get("deletePods", "None"))
 
     def _start_replica(self, mj: ManagedJob, tt: str, idx: int, restarts: int = 0) -> None:
         spec = mj.job.cluster_spec(tt.lower(), idx)
@@ -245,14 +259,16 @@ class Controller:
             self.free_gpus.sort()
             r.gpu = None
 
-    def _finish(self, mj: ManagedJob) -> None:
-        policy = mj.job.to_dict()["spec"].get("clenPodPolicy", "None")
+    def _finish(self, mj: ManagedJob, delete_pods: str = "None") -> None:
+        # deletePodsAndServices (job.go:433-460): cleanPodPolicy None keeps everything, Running / All
+        # stop what is still running (finished processes have nothing left to delete on one box)
         for reps in mj.replicas.values():
             for r in reps.values():
-                if r.proc and r.proc.poll() is None and policy == "Running":
+                if r.proc and r.proc.poll() is None and delete_pods in ("Running", "All"):
                     try:
                         os.killpg(r.proc.pid, signal.SIGTERM)
-                    except ProcessLookupError:
+                        r.proc.wait(timeout=10)
+                    except (ProcessLookupError, subprocess.TimeoutExpired):
                         pass
                 if r.proc and r.proc.poll() is not None:
                     self._release(mj, r)

@@ -7,8 +7,10 @@
 // Reference files are cited per function; where the reference has a latent defect the INTENDED
 // behaviour is implemented and said so.
 #include <stdarg.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include <algorithm>
 #include <atomic>
@@ -727,6 +729,125 @@ int tok_job_update_status(tok_job_t* j, const char* replicas_json, int restartin
     }
   }
   return out ? out_json(status, out) : TOK_OK;
+}
+
+// ---- termination policies (controllers/common/job.go:100-200, 385-460, 511-539) -------------------------
+static bool parse_rfc3339(const std::string& t, double* out) {
+  int Y, M, D, h, m, sec;
+  if (sscanf(t.c_str(), "%d-%d-%dT%d:%d:%d", &Y, &M, &D, &h, &m, &sec) != 6) return false;
+  struct tm tmv;
+  memset(&tmv, 0, sizeof(tmv));
+  tmv.tm_year = Y - 1900;
+  tmv.tm_mon = M - 1;
+  tmv.tm_mday = D;
+  tmv.tm_hour = h;
+  tmv.tm_min = m;
+  tmv.tm_sec = sec;
+  *out = static_cast<double>(timegm(&tmv));
+  return true;
+}
+
+int tok_job_check_termination(tok_job_t* j, const char* replicas_json, int prev_retries,
+                              const char* now_c, char** out) {
+  if (!j || !now_c) return fail(TOK_ERR_INVALID, "job / now is null");
+  status_of(j);
+  const Value* specs = task_specs(j);
+  if (!specs) return fail(TOK_ERR_INVALID, "spec.torchTaskSpecs is missing");
+  Value reps;
+  std::string err;
+  if (!json::parse(replicas_json ? replicas_json : "{}", &reps, &err) || !reps.is_object())
+    return fail(TOK_ERR_INVALID, "replicas must be a JSON object {taskType: [{phase,restartCount}]}: %s", err.c_str());
+  double now = 0;
+  if (!parse_rfc3339(now_c, &now)) return fail(TOK_ERR_INVALID, "now must be RFC3339 (YYYY-MM-DDTHH:MM:SSZ): %s", now_c);
+  const std::string name = job_name(j);
+  const Value* spec = j->doc.find("spec");
+  Value& status = status_of(j);
+
+  int64_t expected = 0, active = 0, failed = 0, restarts = 0, prev_failed = 0;
+  for (const auto& kv : specs->o) {
+    expected += num_tasks(kv.second);  // GetTotalTasks (pkg/utils/utils.go:30-37)
+    const std::string rp = kv.second.find("restartPolicy") ? kv.second.find("restartPolicy")->as_string() : "";
+    const Value* list = nullptr;
+    for (const auto& rk : reps.o)
+      if (equal_fold(rk.first, kv.first)) list = &rk.second;
+    if (!list || !list->is_array()) continue;
+    for (const Value& r : list->a) {
+      const std::string ph = r.find("phase") ? r.find("phase")->as_string() : "";
+      if (ph == "Pending" || ph == "Running") active++;  // k8scontroller.IsPodActive
+      if (ph == "Failed") failed++;
+      if (ph == "Running" && (rp == "OnFailure" || rp == "Always"))  // pastBackoffLimit :385-419
+        restarts += r.find("restartCount") ? r.find("restartCount")->as_int() : 0;
+    }
+  }
+  const Value* ts = status.find("taskStatuses");
+  if (ts && ts->is_object())
+    for (const auto& kv : ts->o)
+      prev_failed += kv.second.find("failed") ? kv.second.find("failed")->as_int() : 0;
+
+  bool exceeds = false, past = false, deadline = false;
+  const Value* bl = spec ? spec->find("backoffLimit") : nullptr;
+  if (bl && bl->is_number()) {
+    const int64_t limit = bl->as_int();
+    exceeds = failed > prev_failed && active != expected && (static_cast<int64_t>(prev_retries) + 1) > limit;
+    past = limit == 0 ? restarts > 0 : restarts >= limit;
+  }
+  std::string failure;
+  bool exceeds_limit = false;
+  if (exceeds || past) {
+    exceeds_limit = true;
+    failure = "Job " + name + " has failed because it has reached the specified backoff limit";
+  } else {
+    const Value* ad = spec ? spec->find("activeDurations") : nullptr;
+    const Value* st = status.find("startTime");
+    double start = 0;
+    if (ad && ad->is_number() && st && st->is_string() && parse_rfc3339(st->s, &start) &&
+        now - start >= static_cast<double>(ad->as_int())) {  // pastActiveDeadline :422-430
+      deadline = true;
+      exceeds_limit = true;
+      failure = "Job " + name + " has failed because it was no longer active";
+      // the reference overwrites CompletionTime on EVERY pass past the deadline (job.go:131-132), so
+      // its TTL clock never starts; intended: stamp it once
+      if (!status.find("completionTime") || status.find("completionTime")->is_null())
+        status["completionTime"] = Value::str(now_c);
+    }
+  }
+  const bool terminate = has_condition(status, "Succeeded") || has_condition(status, "Failed") || exceeds_limit;
+  Value res = Value::object();
+  res["terminate"] = Value::boolean(terminate);
+  res["exceedsBackoffLimit"] = Value::boolean(exceeds);
+  res["pastBackoffLimit"] = Value::boolean(past);
+  res["pastActiveDeadline"] = Value::boolean(deadline);
+  if (terminate) {
+    const std::string policy = (spec && spec->find("clenPodPolicy")) ? spec->find("clenPodPolicy")->as_string() : "None";
+    res["deletePods"] = Value::str(policy == "None" || policy.empty() ? "None" : (policy == "Running" ? "Running" : "All"));
+    if (exceeds_limit) {
+      if (!status.find("completionTime") || status.find("completionTime")->is_null())
+        status["completionTime"] = Value::str(now_c);
+      set_condition(status, "Failed", "JobFailed", failure, now_c);
+      res["message"] = Value::str(failure);
+    }
+    if (has_condition(status, "Succeeded")) {  // job.go:176-184: fold still-active replicas into succeed
+      Value* tsm = status.find("taskStatuses");
+      if (tsm && tsm->is_object())
+        for (auto& kv : tsm->o) {
+          const int64_t a = kv.second.find("active") ? kv.second.find("active")->as_int() : 0;
+          const int64_t sc = kv.second.find("succeed") ? kv.second.find("succeed")->as_int() : 0;
+          kv.second["succeed"] = Value::integer(sc + a);
+          kv.second["active"] = Value::integer(0);
+        }
+    }
+    // cleanupJob (:511-539): TTL after the completion time
+    const Value* ttl = spec ? spec->find("TTLSecondsAfterFinished") : nullptr;
+    const Value* ct = status.find("completionTime");
+    double done = 0;
+    if (ttl && ttl->is_number() && ct && ct->is_string() && parse_rfc3339(ct->s, &done)) {
+      const double del = done + static_cast<double>(ttl->as_int());
+      res["deleteJob"] = Value::boolean(now > del);
+      res["requeueAfter"] = Value::number(now > del ? 0.0 : del - now);
+    }
+  }
+  res["status"] = status;
+  return out_json(res, out);
 }
 
 }  // extern "C"

@@ -83,6 +83,11 @@ class TorchJob:
         return call_json(lib().tok_job_update_status, self._h, json.dumps(replicas).encode(),
                          int(restarting), now.encode())
 
+    # termination policies of ReconcileJobs (backoffLimit / activeDurations / cleanPodPolicy / TTL)
+    def check_termination(self, replicas: Dict[str, List[dict]], prev_retries: int, now: str) -> dict:
+        return call_json(lib().tok_job_check_termination, self._h, json.dumps(replicas).encode(),
+                         prev_retries, now.encode())
+
     def set_condition(self, ctype: str, reason: str, message: str, now: str) -> None:
         check(lib().tok_job_set_condition(self._h, ctype.encode(), reason.encode(),
                                           message.encode(), now.encode()))
