@@ -39,7 +39,7 @@ def manifest(name, port, workers=1, queue=None, restart=None):
 
 def test_mlp_torchjob_world2_matches_golden(tok_lib, tmp_path, monkeypatch):
     monkeypatch.setenv("OUT_DIR", str(tmp_path))
-    ctl = Controller(num_gpus=2, log_dir=str(tmp_path / "logs"))
+    ctl = Controller(num_gpus=2, log_dir=str(tmp_path / "logs"), state_dir=str(tmp_path / "state"))
     uid = ctl.submit(manifest("mnist", free_port()))
     res = ctl.run_until_done(timeout=180)
     assert res[uid] == "Succeeded", (res, ctl.events[-5:])
@@ -57,6 +57,18 @@ def test_mlp_torchjob_world2_matches_golden(tok_lib, tmp_path, monkeypatch):
     st = ctl.jobs[uid].job.status
     assert st["taskStatuses"]["Master"]["succeed"] == 1 and st["taskStatuses"]["Worker"]["succeed"] == 1
     assert len(ctl.free_gpus) == 2
+    # kubectl-shaped views (printer columns of torchjob_types.go:320-324)
+    import io
+    from torch_on_k8s_b200 import cli
+    buf = io.StringIO()
+    assert cli.cmd_get(str(tmp_path / "state"), out=buf) == 0
+    lines = buf.getvalue().splitlines()
+    assert lines[0].split() == ["NAME", "STATE", "AGE", "MODEL-VERSION", "MAX-LIFETIME", "TTL-AFTER-FINISHED"]
+    assert lines[1].split()[:2] == ["mnist", "Succeeded"]
+    buf = io.StringIO()
+    assert cli.cmd_describe(str(tmp_path / "state"), "mnist", out=buf) == 0
+    assert "JobSucceeded" in buf.getvalue() and "succeed=1" in buf.getvalue()
+    assert cli.cmd_describe(str(tmp_path / "state"), "nope", out=io.StringIO()) == 1
     text = ctl.metrics.render()      # the reference's metric names (pkg/metrics/metrics.go)
     assert 'torch_on_k8s_jobs_created_total{kind="TorchJob"} 1.0' in text
     assert 'torch_on_k8s_jobs_successful_total{kind="TorchJob"} 1.0' in text

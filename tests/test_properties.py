@@ -142,3 +142,22 @@ def test_bucket_assignment_matches_torch_reducer():
               (2 << 20, torch.bfloat16), (5, torch.float32), (9 << 20, torch.float32)]]
     check(mixed, caps)
     check(mixed, [1 << 20])
+
+
+def test_bert_base_bucket_sizes_match_survey():
+    """BASELINE configs 2/3: BERT-base bf16 gradient buckets: 8 buckets,
+    218,964,480 bytes per step per replica."""
+    pytest.importorskip("transformers")
+    import torch
+    import torch.distributed as dist
+    from torch_on_k8s_b200.elastic_dp import bucket_assignment
+    from workloads.bert import bert_base
+    params = [p for p in bert_base().to(torch.bfloat16).parameters() if p.requires_grad][::-1]
+    assert sum(p.numel() for p in params) == 109482240 and len(params) == 199
+    caps = [1 << 20, 25 << 20]
+    got = bucket_assignment([p.numel() * 2 for p in params], [(p.dtype, p.device) for p in params], caps)
+    want, _ = dist._compute_bucket_assignment_by_size(params, caps)
+    assert got == want
+    sizes = [sum(params[i].numel() * 2 for i in b) for b in got]
+    assert sizes == [1181184, 27170304, 27170304, 27170304, 27167232, 28351488, 28351488, 52402176]
+    assert sum(sizes) == 218964480

@@ -1,3 +1,5 @@
-from .controller import main
 import sys
+
+from .cli import main
+
 sys.exit(main())

@@ -67,7 +67,7 @@ class ManagedJob:
 
 class Controller:
     def __init__(self, num_gpus: int = 8, *, policy: str = "wrr", log_dir: Optional[str] = None,
-                 rdzv_dir: str = "/tmp"):
+                 rdzv_dir: str = "/tmp", state_dir: Optional[str] = None):
         self.free_gpus = list(range(num_gpus))
         self.num_gpus = num_gpus
         self.coord = Coordinator(policy=policy)
@@ -78,6 +78,7 @@ class Controller:
         self.events: List[tuple] = []
         self.metrics = Metrics()
         self._t_created: Dict[str, float] = {}
+        self.state_dir = state_dir
 
     # ---- submit (owner create) -------------------------------------------------------------------
     def submit(self, manifest, command: Optional[List[str]] = None) -> str:
@@ -88,17 +89,34 @@ class Controller:
         job.set_condition("Created", "JobCreated", "TorchJob %s is created." % job.name, _now())
         mj = ManagedJob(job=job, uid=uid, command=command)
         self.jobs[uid] = mj
+        self._t_created[uid] = time.time()
         if job.need_enqueue():
             self.coord.enqueue(job, uid)
             job.set_condition("Queuing", "JobEnqueued",
                               "Job %s is queuing and waiting for being scheduled." % uid, _now())
         self._event(uid, "JobEnqueued")
         self.metrics.created.labels(KIND).inc()
-        self._t_created[uid] = time.time()
         return uid
 
     def _event(self, uid, reason, msg=""):
         self.events.append((time.time(), uid, reason, msg))
+        self._persist(uid)
+
+    def _persist(self, uid) -> None:
+        """Job object + status for `python -m torch_on_k8s_b200 get/describe` (cli.py)."""
+        if not self.state_dir or uid not in self.jobs:
+            return
+        import json
+        os.makedirs(self.state_dir, exist_ok=True)
+        d = self.jobs[uid].job.to_dict()
+        d["metadata"].setdefault("creationTimestamp", time.strftime(
+            "%Y-%m-%dT%H:%M:%SZ", time.gmtime(self._t_created.get(uid, time.time()))))
+        d["x-events"] = [(time.strftime("%H:%M:%S", time.gmtime(t)), r, m)
+                         for t, u, r, m in self.events if u == uid][-20:]
+        tmp = os.path.join(self.state_dir, uid.replace("/", ".") + ".json")
+        with open(tmp + ".tmp", "w") as f:
+            json.dump(d, f)
+        os.replace(tmp + ".tmp", tmp)
 
     # ---- one controller pass ------------------------------------------------------------------------
     def tick(self, now: Optional[float] = None) -> None:
@@ -306,9 +324,10 @@ def main(argv=None) -> int:
     ap.add_argument("--policy", default="wrr", choices=["rr", "wrr"])
     ap.add_argument("--command", default=None, help="override the replica command (shell-split)")
     ap.add_argument("--log-dir", default=None)
+    ap.add_argument("--state-dir", default=os.environ.get("TOK8S_STATE_DIR"))
     ap.add_argument("--timeout", type=float, default=3600)
     a = ap.parse_args(argv)
-    ctl = Controller(a.gpus, policy=a.policy, log_dir=a.log_dir)
+    ctl = Controller(a.gpus, policy=a.policy, log_dir=a.log_dir, state_dir=a.state_dir)
     for m in a.manifests:
         ctl.submit(load_manifest(m), shlex.split(a.command) if a.command else None)
     res = ctl.run_until_done(a.timeout)
