@@ -161,3 +161,37 @@ def test_bert_base_bucket_sizes_match_survey():
     sizes = [sum(params[i].numel() * 2 for i in b) for b in got]
     assert sizes == [1181184, 27170304, 27170304, 27170304, 27167232, 28351488, 28351488, 52402176]
     assert sum(sizes) == 218964480
+
+
+def test_elastic_dp_bucket_layout_on_cpu(monkeypatch):
+    """ElasticDataParallel's bucket layout logic, with the symmetric-pool allocation stubbed out so
+    that it runs without a GPU: grads become views of the flat buckets, in Reducer order, 16-byte
+    aligned; accumulating into them and zero_grad() keep them views."""
+    import torch
+    from torch_on_k8s_b200 import elastic_dp
+    from workloads.mlp import batch, mlp
+    allocs = []
+
+    def fake_symm(comm, numel, dtype):
+        t = torch.zeros(numel, dtype=dtype)
+        allocs.append(t)
+        return t
+    monkeypatch.setattr(elastic_dp, "symm_tensor", fake_symm)
+    model = mlp(0)
+    edp = elastic_dp.ElasticDataParallel(model, comm=None, bucket_cap_mb=25)
+    assert len(edp.buckets) == 1 and edp.buckets[0] is allocs[0]
+    params = list(model.parameters())[::-1]
+    off = 0
+    for p in params:
+        assert p.grad.data_ptr() == edp.buckets[0].data_ptr() + off * 4 and off % 4 == 0
+        off += (p.numel() + 7) // 8 * 8
+    x, y = batch(0, 8)
+    torch.nn.functional.cross_entropy(edp(x), y).backward()
+    assert all(p.grad.data_ptr() >= edp.buckets[0].data_ptr() for p in params)   # still views
+    assert float(edp.buckets[0].abs().sum()) > 0
+    edp.zero_grad()
+    assert float(edp.buckets[0].abs().sum()) == 0 and params[0].grad is not None
+    # a tiny cap forces several buckets, in the Reducer's order
+    model2 = mlp(0)
+    edp2 = elastic_dp.ElasticDataParallel(model2, comm=None, bucket_cap_mb=0, first_bucket_mb=0)
+    assert len(edp2.buckets) == 4
