@@ -109,7 +109,8 @@ int tok_comm_reform(tok_comm_t* comm, int new_world, int new_rank, uint64_t memb
 /* Unblocks kernels of this replica that spin in a barrier (e.g. a peer died): they exit and the
  * next tok_comm_status() reports TOK_ERR_ABORTED.  Async-signal-unsafe but thread-safe. */
 int tok_comm_abort(tok_comm_t* comm);
-/* 0 while healthy; TOK_ERR_TIMEOUT / TOK_ERR_ABORTED once a kernel gave up. Does not synchronise. */
+/* 0 while healthy; TOK_ERR_TIMEOUT / TOK_ERR_ABORTED once a kernel gave up, TOK_ERR_STATE when a
+ * zero-copy bucket was not at the same pool offset on every replica.  Does not synchronise. */
 int tok_comm_status(tok_comm_t* comm);
 int tok_comm_destroy(tok_comm_t* comm);
 int tok_comm_caps(tok_comm_t* comm, tok_caps_t* caps);
@@ -119,7 +120,9 @@ int tok_comm_caps(tok_comm_t* comm, tok_caps_t* caps);
  * cast_wire(in_r) with the sum multiplied by `scale` (POST).  in == out allowed.  `count` elements;
  * pointers must be 16-byte aligned device pointers of this replica's GPU.  Buckets larger than
  * caps.staging_bytes are split into several launches.  Collective: every replica must issue the
- * same sequence of calls with the same count / dtypes / flags. */
+ * same sequence of calls with the same count / dtypes / flags.  Buckets that live in the symmetric
+ * pool (below) are exchanged in place without staging; that path multiplies the SUM by `scale`
+ * (POST) whatever the flag says — bit-identical to PRE for power-of-two worlds. */
 int tok_allreduce_bucket(tok_comm_t* comm, const void* in, void* out, size_t count, int in_dtype,
                          int wire_dtype, int out_dtype, float scale, unsigned flags,
                          void* cuda_stream);
