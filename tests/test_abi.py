@@ -36,6 +36,21 @@ def test_version_and_error_plumbing(tok_lib):
     assert rc == _ffi.TOK_ERR_INVALID and "rank" in _ffi.last_error()
 
 
+def test_null_and_invalid_arguments_are_rejected(tok_lib):
+    from torch_on_k8s_b200 import _ffi
+    assert tok_lib.tok_allreduce_bucket(None, None, None, 8, 0, 0, 0, 1.0, 0, None) == _ffi.TOK_ERR_INVALID
+    assert tok_lib.tok_comm_status(None) == _ffi.TOK_ERR_INVALID
+    assert tok_lib.tok_comm_destroy(None) == _ffi.TOK_OK
+    assert tok_lib.tok_job_default(None) == _ffi.TOK_ERR_INVALID
+    h = ctypes.c_void_p()
+    assert tok_lib.tok_job_parse(None, ctypes.byref(h)) == _ffi.TOK_ERR_INVALID
+    assert tok_lib.tok_coord_create(7, 0, 1, ctypes.byref(h)) == _ffi.TOK_ERR_INVALID
+    assert tok_lib.tok_pool_malloc(1 << 20, 0, None) is None      # no communicator selected
+    s = ctypes.c_char_p()
+    assert tok_lib.tok_elastic_parse_log(b"not a progress line", ctypes.byref(s)) == _ffi.TOK_ERR_INVALID
+    assert "torchelastic training log" in _ffi.last_error()
+
+
 def test_no_cpu_fallback(tok_lib):
     import torch
     if torch.cuda.is_available():
