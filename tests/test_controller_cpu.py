@@ -151,3 +151,61 @@ def test_active_deadline_terminates_and_cleans_running_replicas(tok_lib, tmp_pat
     assert any("no longer active" in e[3] for e in ctl.events if e[2] == "JobFailed")
     assert len(ctl.free_gpus) == 2
     assert all(r.proc.poll() is not None for reps in ctl.jobs[uid].replicas.values() for r in reps.values())
+
+
+def test_torchelastic_loop_scales_workers_and_publishes_membership(tok_lib, tmp_path, monkeypatch):
+    """a8 end to end on the host side: log scraping -> policy (min 1, max 2: rule 13 doubles after
+    5 samples, then ReachMaxReplicas) -> a new worker replica is created, nobody is restarted, and
+    the membership epoch file announces the new world."""
+    monkeypatch.setenv("RUN_S", "7")
+    m = manifest("el", free_port())
+    for tt in ("Master", "Worker"):
+        m["spec"]["torchTaskSpecs"][tt]["template"]["spec"]["containers"][0]["command"] = \
+            [sys.executable, os.path.join(HERE, "cpu_elastic_replica.py")]
+    m["spec"]["enableTorchElastic"] = True
+    m["spec"]["torchElasticPolicy"] = {"rendezvousBackend": "c10d", "rendezvousEndpoint": "x",
+                                       "numMinReplicas": 1, "numMaxReplicas": 2}
+    ctl = Controller(num_gpus=3, log_dir=str(tmp_path / "logs"), rdzv_dir=str(tmp_path),
+                     elastic_period=0.25)
+    uid = ctl.submit(m)
+    res = ctl.run_until_done(timeout=90)
+    assert res[uid] == "Succeeded", ctl.events[-8:]
+    scale = [e for e in ctl.events if e[2] == "ElasticScale"]
+    assert len(scale) == 1 and "Worker 1 -> 2" in scale[0][3]
+    pods = [e[3] for e in ctl.events if e[2] == "SuccessfulCreatePod"]
+    assert pods == ["el-master-0", "el-worker-0", "el-worker-1"]          # nobody was restarted
+    members = [json.loads(e[3]) for e in ctl.events if e[2] == "MembershipPublished"]
+    assert members[-1] == {"epoch": 1, "world": 3,
+                           "ranks": {"el-master-0": 0, "el-worker-0": 1, "el-worker-1": 2}}
+    st = ctl.jobs[uid].job.status["elasticScalingStatues"]["Worker"]
+    assert st["elasticCondition"] == "ReachMaxReplicas" and st["curReplicas"] == 2
+    # the torchrun args contract for the new size (SetClusterSpec :387-392)
+    assert ctl.jobs[uid].job.cluster_spec("worker", 1)["env"][2] == {"name": "RANK", "value": "2"}
+
+
+def test_torchelastic_revert_scales_in_and_deletes_out_of_range_replica(tok_lib, tmp_path, monkeypatch):
+    """Scale-out that makes the per-replica latency worse is reverted (rule 12, ReachMaxMetric): the
+    out-of-range replica is deleted (reconcileOnePod, pod.go:648-651), its GPU slot freed, the
+    survivors keep running, and a second membership epoch announces the smaller world."""
+    monkeypatch.setenv("RUN_S", "8")
+    monkeypatch.setenv("ADAPTIVE", "1")
+    m = manifest("si", free_port())
+    for tt in ("Master", "Worker"):
+        m["spec"]["torchTaskSpecs"][tt]["template"]["spec"]["containers"][0]["command"] = \
+            [sys.executable, os.path.join(HERE, "cpu_elastic_replica.py")]
+    m["spec"]["enableTorchElastic"] = True
+    m["spec"]["torchElasticPolicy"] = {"rendezvousBackend": "c10d", "rendezvousEndpoint": "x",
+                                       "numMinReplicas": 1, "numMaxReplicas": 2}
+    ctl = Controller(num_gpus=3, rdzv_dir=str(tmp_path), log_dir=str(tmp_path / "logs"),
+                     elastic_period=0.25)
+    uid = ctl.submit(m)
+    res = ctl.run_until_done(timeout=90)
+    assert res[uid] == "Succeeded", ctl.events[-8:]
+    scale = [e[3] for e in ctl.events if e[2] == "ElasticScale"]
+    assert len(scale) == 2 and "scale: Worker 1 -> 2" in scale[0] and "revert: Worker 2 -> 1" in scale[1]
+    assert [e[3] for e in ctl.events if e[2] == "SuccessfulDeletePod"] == ["si-worker-1"]
+    members = [json.loads(e[3]) for e in ctl.events if e[2] == "MembershipPublished"]
+    assert [(d["epoch"], d["world"]) for d in members] == [(1, 3), (2, 2)]
+    assert ctl.jobs[uid].job.num_tasks("Worker") == 1 and len(ctl.free_gpus) == 3
+    st = ctl.jobs[uid].job.status["elasticScalingStatues"]["Worker"]
+    assert st["elasticCondition"] == "Stop" and st["curReplicas"] == 1 and st["lastReplicas"] == 2

@@ -32,6 +32,7 @@ from dataclasses import dataclass, field
 from typing import Dict, List, Optional
 
 from .coordinator import SCHEDULING_PERIOD_S, Coordinator
+from .elastic import LOOP_PERIOD_S, ElasticPolicy, parse_log_line
 from .job import TASK_ORDER, TorchJob, should_failover
 from .metrics import KIND, Metrics
 
@@ -63,11 +64,15 @@ class ManagedJob:
     gpus: List[int] = field(default_factory=list)
     done: bool = False
     retries: int = 0          # BackoffStatesQueue.NumRequeues stand-in (failover passes so far)
+    epoch: int = 0            # membership epoch of the job's peer group (bumped on every rescale)
+    elastic: Optional[ElasticPolicy] = None
+    elastic_due: float = 0.0
 
 
 class Controller:
     def __init__(self, num_gpus: int = 8, *, policy: str = "wrr", log_dir: Optional[str] = None,
-                 rdzv_dir: str = "/tmp", state_dir: Optional[str] = None):
+                 rdzv_dir: str = "/tmp", state_dir: Optional[str] = None,
+                 elastic_period: float = LOOP_PERIOD_S):
         self.free_gpus = list(range(num_gpus))
         self.num_gpus = num_gpus
         self.coord = Coordinator(policy=policy)
@@ -79,6 +84,7 @@ class Controller:
         self.metrics = Metrics()
         self._t_created: Dict[str, float] = {}
         self.state_dir = state_dir
+        self.elastic_period = elastic_period
 
     # ---- submit (owner create) -------------------------------------------------------------------
     def submit(self, manifest, command: Optional[List[str]] = None) -> str:
@@ -169,7 +175,25 @@ class Controller:
             self.coord.job_settled(mj.uid)
             self._finish(mj, term.get("deletePods", "None"))
             return
+        self._elastic_pass(mj)
         specs = job.task_specs
+        # replicas whose index fell out of [0, numTasks) are scaled down (reconcileOnePod,
+        # controllers/common/pod.go:648-651)
+        changed = False
+        for tt, have in mj.replicas.items():
+            n = int(specs.get(tt, {}).get("numTasks", 1)) if tt in specs else 0
+            for idx in [i for i in have if i >= n]:
+                r = have.pop(idx)
+                if r.proc and r.proc.poll() is None:
+                    try:
+                        os.killpg(r.proc.pid, signal.SIGTERM)
+                        r.proc.wait(timeout=10)
+                    except (ProcessLookupError, subprocess.TimeoutExpired):
+                        pass
+                self._release(mj, r)
+                self._event(mj.uid, "SuccessfulDeletePod", "%s-%s-%d" % (job.name, tt.lower(), idx))
+                changed = True
+        before = sum(len(v) for v in mj.replicas.values())
         for tt in TASK_ORDER + [k for k in specs if k not in TASK_ORDER]:
             if tt not in specs:
                 continue
@@ -180,6 +204,9 @@ class Controller:
             for idx in range(int(specs[tt].get("numTasks", 1))):
                 if idx not in have:
                     self._start_replica(mj, tt, idx)
+        if mj.epoch > 0 or changed:
+            if changed or sum(len(v) for v in mj.replicas.values()) != before:
+                self._publish_membership(mj)
         reps = {tt: [dict(phase=r.phase, scheduled=r.gpu is not None or tt == "AIMaster",
                           exitCode=r.exit_code) for r in v.values()]
                 for tt, v in mj.replicas.items()}
@@ -190,6 +217,64 @@ class Controller:
         if last in ("Failed", "Succeeded"):
             term = job.check_termination(pods, mj.retries, _now())
             self._finish(mj, term.get("deletePods", "None"))
+
+    # ---- torchelastic (controllers/train/torchelastic/elastictorchjob_controller.go:142-166) -------
+    def _elastic_pass(self, mj: ManagedJob) -> None:
+        """One decision pass per `elastic_period` for jobs with enableTorchElastic: read the last
+        progress line of <job>-worker-0 (observation.go:40-85), feed the policy, let the normal
+        reconcile create / delete replicas for the new Worker.numTasks.  Survivors are not restarted:
+        they learn the new membership from the epoch file (see _publish_membership)."""
+        spec = mj.job.to_dict()["spec"]
+        if not spec.get("enableTorchElastic") or not spec.get("torchElasticPolicy"):
+            return
+        now = time.monotonic()
+        if now < mj.elastic_due:
+            return
+        mj.elastic_due = now + self.elastic_period
+        if mj.elastic is None:
+            mj.elastic = ElasticPolicy()
+        workers = mj.replicas.get("Worker", {})
+        latency = -1.0
+        w0 = workers.get(0)
+        if w0 is not None and w0.log_path and os.path.exists(w0.log_path):
+            with open(w0.log_path, "rb") as f:
+                lines = f.read().decode("utf-8", "replace").strip().splitlines()
+            if lines:
+                try:
+                    latency = float(parse_log_line(lines[-1])["latency"])
+                except Exception:  # noqa: BLE001 — not a progress line / latency > 1 s: skip the tick
+                    latency = -1.0
+        before = mj.job.num_tasks("Worker")
+        out = mj.elastic.observe(mj.job, latency,
+                                 has_pending=any(r.phase == "Pending" for r in workers.values()),
+                                 has_failed=any(r.phase == "Failed" for r in workers.values()))
+        if out["action"] in ("scale", "revert"):
+            mj.epoch += 1
+            self._event(mj.uid, "ElasticScale", "%s: Worker %d -> %d (%s)" %
+                        (out["action"], before, out["replicas"], out["condition"]))
+        elif out["action"] in ("forget", "stop_managing"):
+            mj.elastic_due = float("inf")
+
+    def _publish_membership(self, mj: ManagedJob) -> None:
+        """Membership epoch file next to the job's rendezvous socket: the in-place replacement of the
+        reference's `distributed.io/world-size` annotation + kruise container restart
+        (controllers/train/elastic_scale.go:303-397).  Replicas poll it (worker.Replica.poll_membership)
+        and call tok_comm_reform / join at the announced epoch."""
+        import json
+        members = {}
+        for tt in TASK_ORDER:
+            for idx in sorted(mj.replicas.get(tt, {})):
+                if tt == "AIMaster":
+                    continue
+                spec = mj.job.cluster_spec(tt.lower(), idx)
+                members[spec["name"]] = spec["rank"]
+        port = mj.job.cluster_spec("master", 0)["env"][0]["value"]
+        path = os.path.join(self.rdzv_dir, "tok8s-%s-%s.members" % (mj.job.name.replace("/", "-"), port))
+        doc = {"epoch": mj.epoch, "world": mj.job.world_size, "ranks": members}
+        with open(path + ".tmp", "w") as f:
+            json.dump(doc, f)
+        os.replace(path + ".tmp", path)
+        self._event(mj.uid, "MembershipPublished", json.dumps(doc))
 
     def _start_replica(self, mj: ManagedJob, tt: str, idx: int, restarts: int = 0) -> None:
         spec = mj.job.cluster_spec(tt.lower(), idx)
@@ -205,7 +290,7 @@ class Controller:
         if env.get("MASTER_ADDR") not in ("localhost", "127.0.0.1"):
             env["MASTER_ADDR"] = "127.0.0.1"   # single box: the master's name resolves to loopback
         env.update(TOK8S_JOB=mj.job.name, TOK8S_REPLICA=spec["name"], TOK8S_TASK_TYPE=tt,
-                   TOK8S_TASK_INDEX=str(idx),
+                   TOK8S_TASK_INDEX=str(idx), TOK8S_EPOCH=str(mj.epoch),
                    TOK8S_RDZV=os.path.join(self.rdzv_dir, "tok8s-%s-%s" %
                                            (mj.job.name.replace("/", "-"), env["MASTER_PORT"])))
         if gpu is not None:

@@ -65,6 +65,35 @@ class Replica:
         ddp.register_comm_hook(None, hook.as_function())
         return ddp, hook
 
+    def poll_membership(self):
+        """Elastic add/drop without a restart: read the membership epoch file the controller writes
+        next to the rendezvous socket (controller.Controller._publish_membership) and, when the epoch
+        moved, re-form the peer group in place (tok_comm_reform).  Returns the new (rank, world) or
+        None when nothing changed / this replica was dropped."""
+        import json
+        path = self.comm.rendezvous_path + ".members"
+        try:
+            with open(path) as f:
+                doc = json.load(f)
+        except (OSError, ValueError):
+            return None
+        if doc["epoch"] <= self.comm.caps().epoch:
+            return None
+        me = os.environ.get("TOK8S_REPLICA", "")
+        if me not in doc["ranks"]:
+            return None
+        old = self.rank
+        mask = 0
+        # survivors = replicas present in both epochs; without the previous table assume every lower
+        # rank that is still listed survived (ranks are assigned master 0, worker i -> i+1)
+        for r in doc["ranks"].values():
+            if r < self.world:
+                mask |= 1 << r
+        mask |= 1 << old
+        self.comm.reform(doc["world"], doc["ranks"][me], mask, doc["epoch"])
+        self.rank, self.world = doc["ranks"][me], doc["world"]
+        return self.rank, self.world
+
     def close(self):
         self.comm.close()
         if dist.is_initialized():
@@ -72,7 +101,7 @@ class Replica:
 
 
 def init_replica(job_id: Optional[str] = None, *, device: Optional[int] = None,
-                 bootstrap_backend: str = "nccl", max_world: int = 8) -> Replica:
+                 bootstrap_backend: Optional[str] = "nccl", max_world: int = 8) -> Replica:
     """Read RANK / WORLD_SIZE / MASTER_* (reference env contract), bind this replica to its GPU,
     join the job's peer group.  torch.distributed is initialised only as plumbing (DDP needs a
     process group for its initial parameter broadcast); gradients never touch it."""
@@ -90,9 +119,12 @@ def init_replica(job_id: Optional[str] = None, *, device: Optional[int] = None,
     torch.cuda.set_device(device)
     dev = torch.device("cuda", device)
     job_id = job_id or os.environ.get("TOK8S_JOB", "torchjob")
-    if not dist.is_initialized():
+    # bootstrap_backend=None: no torch.distributed at all (ElasticDataParallel users, whose world
+    # size changes while the process keeps running)
+    if bootstrap_backend and not dist.is_initialized():
         dist.init_process_group(bootstrap_backend, rank=rank, world_size=world, device_id=dev)
     comm = Communicator(job_id, rank, world, device, max_world=max_world,
                         rendezvous_path=os.environ.get("TOK8S_RDZV") or
-                        default_rendezvous_path(job_id))
+                        default_rendezvous_path(job_id),
+                        epoch=int(os.environ.get("TOK8S_EPOCH", "0")))
     return Replica(rank=rank, world=world, device=dev, comm=comm, job_id=job_id)
