@@ -175,8 +175,13 @@ def test_torchelastic_loop_scales_workers_and_publishes_membership(tok_lib, tmp_
     pods = [e[3] for e in ctl.events if e[2] == "SuccessfulCreatePod"]
     assert pods == ["el-master-0", "el-worker-0", "el-worker-1"]          # nobody was restarted
     members = [json.loads(e[3]) for e in ctl.events if e[2] == "MembershipPublished"]
-    assert members[-1] == {"epoch": 1, "world": 3,
+    assert members[-1] == {"epoch": 1, "world": 3, "survivor_mask": 0b11,
                            "ranks": {"el-master-0": 0, "el-worker-0": 1, "el-worker-1": 2}}
+    from torch_on_k8s_b200.worker import membership_update
+    assert membership_update(members[-1], "el-worker-0", 0) == (3, 1, 0b11, 1)   # survivor re-forms
+    assert membership_update(members[-1], "el-worker-1", 0) == (3, 2, 0b11, 1)   # joiner's view
+    assert membership_update(members[-1], "el-worker-0", 1) is None              # already there
+    assert membership_update(members[-1], "el-worker-9", 0) is None              # not a member
     st = ctl.jobs[uid].job.status["elasticScalingStatues"]["Worker"]
     assert st["elasticCondition"] == "ReachMaxReplicas" and st["curReplicas"] == 2
     # the torchrun args contract for the new size (SetClusterSpec :387-392)
@@ -205,7 +210,7 @@ def test_torchelastic_revert_scales_in_and_deletes_out_of_range_replica(tok_lib,
     assert len(scale) == 2 and "scale: Worker 1 -> 2" in scale[0] and "revert: Worker 2 -> 1" in scale[1]
     assert [e[3] for e in ctl.events if e[2] == "SuccessfulDeletePod"] == ["si-worker-1"]
     members = [json.loads(e[3]) for e in ctl.events if e[2] == "MembershipPublished"]
-    assert [(d["epoch"], d["world"]) for d in members] == [(1, 3), (2, 2)]
+    assert [(d["epoch"], d["world"], d["survivor_mask"]) for d in members] == [(1, 3, 0b11), (2, 2, 0b011)]
     assert ctl.jobs[uid].job.num_tasks("Worker") == 1 and len(ctl.free_gpus) == 3
     st = ctl.jobs[uid].job.status["elasticScalingStatues"]["Worker"]
     assert st["elasticCondition"] == "Stop" and st["curReplicas"] == 1 and st["lastReplicas"] == 2

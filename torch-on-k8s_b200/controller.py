@@ -51,6 +51,7 @@ class ReplicaProc:
     exit_code: Optional[int] = None
     restarts: int = 0
     log_path: Optional[str] = None
+    epoch: int = 0              # membership epoch at which this replica was started
 
 
 @dataclass
@@ -261,16 +262,21 @@ class Controller:
         (controllers/train/elastic_scale.go:303-397).  Replicas poll it (worker.Replica.poll_membership)
         and call tok_comm_reform / join at the announced epoch."""
         import json
-        members = {}
+        members, mask = {}, 0
         for tt in TASK_ORDER:
             for idx in sorted(mj.replicas.get(tt, {})):
                 if tt == "AIMaster":
                     continue
                 spec = mj.job.cluster_spec(tt.lower(), idx)
                 members[spec["name"]] = spec["rank"]
+                # a replica's rank is a function of (task type, index), so a survivor keeps its rank:
+                # bit i set <=> the replica that held rank i before this epoch is still a member
+                # (tok_comm_reform's member_mask)
+                if mj.replicas[tt][idx].epoch < mj.epoch:
+                    mask |= 1 << spec["rank"]
         port = mj.job.cluster_spec("master", 0)["env"][0]["value"]
         path = os.path.join(self.rdzv_dir, "tok8s-%s-%s.members" % (mj.job.name.replace("/", "-"), port))
-        doc = {"epoch": mj.epoch, "world": mj.job.world_size, "ranks": members}
+        doc = {"epoch": mj.epoch, "world": mj.job.world_size, "ranks": members, "survivor_mask": mask}
         with open(path + ".tmp", "w") as f:
             json.dump(doc, f)
         os.replace(path + ".tmp", path)
@@ -305,7 +311,7 @@ class Controller:
         proc = subprocess.Popen(cmd, env=env, stdout=log or None, stderr=subprocess.STDOUT if log else None,
                                 start_new_session=True)
         mj.replicas[tt][idx] = ReplicaProc(tt, idx, gpu, proc, "Running", restarts=restarts,
-                                           log_path=log.name if log else None)
+                                           log_path=log.name if log else None, epoch=mj.epoch)
         self._event(mj.uid, "SuccessfulCreatePod", spec["name"])
         d = mj.job.to_dict()["metadata"]
         lbl = (KIND, d["name"], d.get("namespace", "default"), mj.uid)

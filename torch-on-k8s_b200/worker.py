@@ -68,36 +68,35 @@ class Replica:
     def poll_membership(self):
         """Elastic add/drop without a restart: read the membership epoch file the controller writes
         next to the rendezvous socket (controller.Controller._publish_membership) and, when the epoch
-        moved, re-form the peer group in place (tok_comm_reform).  Returns the new (rank, world) or
-        None when nothing changed / this replica was dropped."""
+        moved, re-form the peer group in place (tok_comm_reform).  Returns the new (rank, world), or
+        None when nothing changed or this replica is no longer a member."""
         import json
-        path = self.comm.rendezvous_path + ".members"
         try:
-            with open(path) as f:
+            with open(self.comm.rendezvous_path + ".members") as f:
                 doc = json.load(f)
         except (OSError, ValueError):
             return None
-        if doc["epoch"] <= self.comm.caps().epoch:
+        step = membership_update(doc, os.environ.get("TOK8S_REPLICA", ""), self.comm.caps().epoch)
+        if step is None:
             return None
-        me = os.environ.get("TOK8S_REPLICA", "")
-        if me not in doc["ranks"]:
-            return None
-        old = self.rank
-        mask = 0
-        # survivors = replicas present in both epochs; without the previous table assume every lower
-        # rank that is still listed survived (ranks are assigned master 0, worker i -> i+1)
-        for r in doc["ranks"].values():
-            if r < self.world:
-                mask |= 1 << r
-        mask |= 1 << old
-        self.comm.reform(doc["world"], doc["ranks"][me], mask, doc["epoch"])
-        self.rank, self.world = doc["ranks"][me], doc["world"]
+        new_world, new_rank, mask, epoch = step
+        self.comm.reform(new_world, new_rank, mask, epoch)
+        self.rank, self.world = new_rank, new_world
         return self.rank, self.world
 
     def close(self):
         self.comm.close()
         if dist.is_initialized():
             dist.destroy_process_group()
+
+
+def membership_update(doc: dict, replica_name: str, current_epoch: int):
+    """Pure decision behind Replica.poll_membership: (new_world, new_rank, member_mask, epoch) for
+    tok_comm_reform, or None when the published epoch is not newer / this replica was dropped."""
+    if int(doc.get("epoch", 0)) <= current_epoch or replica_name not in doc.get("ranks", {}):
+        return None
+    return int(doc["world"]), int(doc["ranks"][replica_name]), int(doc.get("survivor_mask", 0)), \
+        int(doc["epoch"])
 
 
 def init_replica(job_id: Optional[str] = None, *, device: Optional[int] = None,
