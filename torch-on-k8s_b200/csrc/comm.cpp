@@ -342,6 +342,7 @@ struct tok_comm {
   size_t cap_bytes = 0;
   size_t pool_bytes = 0;   // symmetric pool for zero-copy buckets
   size_t pool_used = 0;    // bump pointer (identical allocation sequence on every replica)
+  std::mutex pool_mu;      // tok_pool_malloc may be entered from any allocator-calling thread
   size_t heap_bytes = 0;
   bool zero_copy = true;
   CUmemGenericAllocationHandle local_handle = 0;
@@ -1038,6 +1039,7 @@ int tok_allreduce_algo(tok_comm_t* c, size_t wire_bytes, int* algo) {
 int tok_comm_symm_alloc(tok_comm_t* c, size_t bytes, void** ptr) {
   if (!c || !ptr) return fail(TOK_ERR_INVALID, "comm / ptr is null");
   const size_t need = round_up(std::max<size_t>(bytes, 1), 2u << 20);  // segment-friendly alignment
+  std::lock_guard<std::mutex> lock(c->pool_mu);
   if (c->pool_used + need > c->pool_bytes)
     return fail(TOK_ERR_INVALID,
                 "symmetric pool exhausted: %zu MiB used + %zu MiB requested > %zu MiB (TOK_SYMM_POOL_MB)",
