@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define TOK_ABI_VERSION 1
+#define TOK_ABI_VERSION 2
 #define TOK_MAX_WORLD 8 /* one 8xB200 box: one replica per GPU */
 
 /* ---- error codes ------------------------------------------------------------------------- */
@@ -61,7 +61,9 @@ enum {
   TOK_ALGO_LOCAL = 1,    /* world == 1: fused scale/cast only (HBM bound)                        */
   TOK_ALGO_ONE_SHOT = 2, /* push to every peer, one barrier, local reduce                        */
   TOK_ALGO_TWO_SHOT = 3, /* reduce-scatter + all-gather over peer HBM, two barriers              */
-  TOK_ALGO_NVLS = 4      /* NVSwitch multicast: multimem.ld_reduce + multimem.st                 */
+  TOK_ALGO_NVLS = 4,     /* NVSwitch multicast: multimem.ld_reduce + multimem.st                 */
+  TOK_ALGO_LOCAL_TMA = 7 /* world == 1, one dtype: LOCAL with cp.async.bulk (TMA) through a
+                            shared-memory ring instead of LDG/STG (TOK_LOCAL_TMA=1 makes AUTO pick it) */
 };
 
 /* flags for tok_allreduce_bucket */
@@ -69,6 +71,11 @@ enum {
                                  /* out = cast(sum(wire(in * scale))) == built-in DDP (mul by 1/N
                                     then sum)                                    */
 #define TOK_FLAG_NO_ZERO_COPY 0x2u /* always stage, even for buckets in the symmetric pool        */
+#define TOK_FLAG_ARRIVED 0x4u    /* tok_bucket_arrive() was already enqueued for this bucket on this
+                                    stream: do not enqueue a second arrival                       */
+#define TOK_FLAG_NO_ELIDE 0x8u   /* world == 1: launch the fused scale/cast even when it would be an
+                                    identity (in == out, one dtype, scale 1) — by default such a bucket
+                                    costs no launch and no HBM pass                               */
 #define TOK_FLAG_ALGO_SHIFT 8    /* (TOK_ALGO_x << TOK_FLAG_ALGO_SHIFT) forces an algorithm      */
 #define TOK_FLAG_ALGO_MASK 0xF00u
 
@@ -121,11 +128,34 @@ int tok_comm_caps(tok_comm_t* comm, tok_caps_t* caps);
  * pointers must be 16-byte aligned device pointers of this replica's GPU.  Buckets larger than
  * caps.staging_bytes are split into several launches.  Collective: every replica must issue the
  * same sequence of calls with the same count / dtypes / flags.  Buckets that live in the symmetric
- * pool (below) are exchanged in place without staging; that path multiplies the SUM by `scale`
- * (POST) whatever the flag says — bit-identical to PRE for power-of-two worlds. */
+ * pool (below) are exchanged in place without staging: a 1-warp arrival kernel ("my bucket is ready",
+ * wait for every peer's, symmetry check) followed by the exchange kernel.  The P2P in-place kernel
+ * honours PRE/POST exactly like the staged path (bit-identical to it); the NVSwitch (NVLS) in-place
+ * kernel can only scale the sum, so AUTO uses it when that is the same function — POST, or `scale`
+ * a power of two (1/N for N = 2, 4, 8) — and never for an f16 PRE bucket (the sum could overflow
+ * before it is scaled); otherwise AUTO takes the P2P in-place kernel. */
 int tok_allreduce_bucket(tok_comm_t* comm, const void* in, void* out, size_t count, int in_dtype,
                          int wire_dtype, int out_dtype, float scale, unsigned flags,
                          void* cuda_stream);
+
+/* Split form of the zero-copy exchange, for callers that want the wait for the slowest replica and
+ * the exchange itself as separate stream operations (bench.py times the exchange alone; a DDP hook
+ * can enqueue the arrival as soon as the bucket is produced).  Enqueues the arrival kernel for
+ * `bucket` (count elements of `dtype`, exchanged in place with `scale` / `flags` as the later
+ * tok_allreduce_bucket call will pass them) when — and only when — that call will take a zero-copy
+ * kernel; *arrived tells which.  When it is 1, pass TOK_FLAG_ARRIVED to tok_allreduce_bucket.
+ * The arrival occupies ONE warp while it waits, not an exchange grid. */
+int tok_bucket_arrive(tok_comm_t* comm, const void* bucket, size_t count, int dtype, float scale,
+                      unsigned flags, void* cuda_stream, int* arrived);
+
+/* Replicates `bytes` bytes at `buf` of replica `root` into `buf` of every replica: the initial
+ * parameter broadcast and the state hand-over to replicas that join at an elastic re-form (replaces
+ * dist._broadcast_coalesced, torch/nn/parallel/distributed.py:1032; reference trigger:
+ * controllers/train/elastic_scale.go:303-340).  Buffers in the symmetric pool are written in place —
+ * by ONE multimem.st stream of the root through the NVSwitch when a multicast object is bound, else
+ * pulled by the receivers over NVLink; any other 16-byte aligned device buffer goes through the
+ * root's staging buffer.  Collective, stream-ordered, bit-exact copy. */
+int tok_broadcast(tok_comm_t* comm, void* buf, size_t bytes, int root, void* cuda_stream);
 
 /* Symmetric pool (zero-copy buckets).  Memory returned by tok_comm_symm_alloc lives inside this
  * replica's heap; when EVERY replica performs the same sequence of allocations, a bucket has the
@@ -136,6 +166,9 @@ int tok_allreduce_bucket(tok_comm_t* comm, const void* in, void* out, size_t cou
  * communicator selected by tok_comm_use_as_pool(), so that a torch.cuda.MemPool — and with it
  * DistributedDataParallel's bucket storage — can live in the pool.                              */
 int tok_comm_symm_alloc(tok_comm_t* comm, size_t bytes, void** ptr);
+/* Returns a segment to the pool (first-fit free list, neighbours merged).  Like allocation, release
+ * must happen in the same order on every replica. */
+int tok_comm_symm_free(tok_comm_t* comm, void* ptr, size_t bytes);
 int tok_comm_symm_info(tok_comm_t* comm, void** base, size_t* bytes, size_t* used);
 int tok_comm_use_as_pool(tok_comm_t* comm);
 void* tok_pool_malloc(ptrdiff_t size, int device, void* cuda_stream);
@@ -143,8 +176,20 @@ void tok_pool_free(void* ptr, size_t size, int device, void* cuda_stream);
 
 /* Which algorithm AUTO picks for `wire_bytes` on this communicator. */
 int tok_allreduce_algo(tok_comm_t* comm, size_t wire_bytes, int* algo);
-/* Number of kernels this communicator has launched so far (bench.py's gpu_launches). */
+/* Number of kernels this communicator has launched so far (bench.py's gpu_launches): exchange,
+ * local, broadcast and arrival kernels. */
 int tok_comm_launches(tok_comm_t* comm, uint64_t* launches);
+
+typedef struct tok_stats {
+  uint64_t launches;   /* exchange / local / broadcast kernels                                    */
+  uint64_t arrivals;   /* 1-warp arrival kernels                                                  */
+  uint64_t elided;     /* world-1 identity buckets that needed no launch                          */
+  uint64_t broadcasts; /* tok_broadcast calls                                                     */
+  int last_algo;       /* kernel of the last launch: TOK_ALGO_* or 5 two-shot in place, 6 NVLS in
+                          place, 16 broadcast multicast push, 17 broadcast pull, 18 broadcast staged */
+  int last_ctas;       /* its grid size                                                           */
+} tok_stats_t;
+int tok_comm_stats(tok_comm_t* comm, tok_stats_t* stats);
 
 /* Profiling aid: with TOK_DEBUG_PHASES=1 in the environment at tok_comm_create, every exchange
  * kernel records per-CTA globaltimer stamps [cta][8] = {start, staged, barrierA, reduced, barrierB,

@@ -77,9 +77,10 @@ def _build(workload: str):
         from workloads.mlp import mlp
         return mlp(0)
     if workload == "resnet50":
-        from workloads.resnet50 import resnet50
+        # stock torchvision model: the reference arm shares no model code with the product side
+        from torchvision.models import resnet50
         torch.manual_seed(0)
-        return resnet50()
+        return resnet50(num_classes=1000)
     raise ValueError(workload)
 
 
@@ -95,8 +96,30 @@ def _batch(workload: str, rank: int, n: int, dtype):
     return x, y
 
 
+# Everything a launcher (torchrun, a test runner, a scheduler) may have left in the environment
+# that changes how init_process_group("gloo", "env://") or OpenMP behave.  The reference writes ONLY
+# the SetClusterSpec variables into a container (torchjob_controller.go:394-446): nothing else is
+# inherited.  With TORCHELASTIC_USE_AGENT_STORE set, env:// waits for an agent store nobody started.
+_SCRUB_PREFIXES = ("TORCHELASTIC_", "GROUP_", "ROLE_", "LOCAL_", "NCCL_", "TORCH_NCCL_", "OMP_",
+                   "MKL_", "KMP_", "GOMP_", "TORCHINDUCTOR_", "PET_", "TOK8S_", "TOK_")
+_SCRUB_KEYS = ("RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT", "PYTHONUNBUFFERED")
+
+
+def clean_env(extra: Dict[str, str]) -> Dict[str, str]:
+    """The environment of one replica container: the caller's environment minus everything a
+    launcher injected, plus the SetClusterSpec variables in `extra`."""
+    env = {k: v for k, v in os.environ.items()
+           if not k.startswith(_SCRUB_PREFIXES) and k not in _SCRUB_KEYS}
+    env["PYTHONPATH"] = ROOT + (os.pathsep + env["PYTHONPATH"] if env.get("PYTHONPATH") else "")
+    env.update(extra)
+    return env
+
+
 def _replica(rank, world, env, workload, steps, warmup, batch, threads, dtype_name, dump, q):
     try:
+        for k in list(os.environ):
+            if k.startswith(_SCRUB_PREFIXES) or k in _SCRUB_KEYS:
+                del os.environ[k]
         os.environ.update(env)
         # single box: the master's service name resolves to loopback
         os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -123,7 +146,9 @@ def _replica(rank, world, env, workload, steps, warmup, batch, threads, dtype_na
                     return out
                 return fut.then(done)
             ddp.register_comm_hook(None, hook)
-        opt = torch.optim.SGD(ddp.parameters(), lr=0.01)
+        # same optimizer as the product arm of bench.py for ResNet-50; plain SGD for the MLP goldens
+        opt = torch.optim.SGD(ddp.parameters(), lr=0.01,
+                              momentum=0.9 if workload == "resnet50" else 0.0)
         lossf = torch.nn.CrossEntropyLoss()
         x, y = _batch(workload, rank, batch, dtype)
         losses = []
@@ -165,7 +190,9 @@ def run(workload: str = "mlp", world: int = 2, steps: int = 5, warmup: int = 1, 
     """Run the gloo/CPU torchjob with `world` replicas (1 master + world-1 workers) and return
     {"seconds", "steps", "images_per_sec", "cores", "threads_per_replica", "losses"}."""
     cores = effective_cores()
-    threads = threads or max(1, cores // world)
+    # cores are split between the replicas; more than 16 threads per replica only adds OpenMP
+    # spinning at these batch sizes (measured: 96 threads 23 img/s vs 16 threads 74 img/s)
+    threads = threads or max(1, min(cores // world, 16))
     port = free_port()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()

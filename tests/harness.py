@@ -108,12 +108,13 @@ def run_cases(rank: int, world: int, device: int, path: str, cases: List[dict],
             seed = case.get("seed", 1234 + ci)
             inplace = case.get("inplace", din == dout)
             symm = case.get("symm", False)        # bucket allocated in the symmetric pool: zero-copy
-            if symm:
-                post = True                       # the in-place kernels scale the sum
             if algo == 4 and not caps.multicast:
                 results.append(dict(case=case, skipped="no multicast"))
                 continue
             if algo == 1 and world != 1:
+                continue
+            if case.get("bcast") is not None:
+                results.append(_run_bcast(comm, case, rank, world, dev, stream, ci))
                 continue
             inputs = [gen_input(seed, r, count, din, pattern) for r in range(world)]
             want = allreduce_oracle(inputs, din, dw, dout, scale, post)
@@ -129,8 +130,13 @@ def run_cases(rank: int, world: int, device: int, path: str, cases: List[dict],
                     x = to_torch(inputs[rank], din, dev)
                     y = x if inplace else torch.empty(count, dtype=torch_dtype(dout), device=dev)
                 t0 = time.perf_counter()
+                arrived = False
+                if case.get("split"):   # the two-call form: arrival kernel, then the exchange
+                    arrived = comm.bucket_arrive(x, scale=scale, post_scale=post, algo=algo,
+                                                 stream=stream)
                 comm.allreduce_bucket(x, y, scale=scale, wire_dtype=torch_dtype(dw),
-                                      post_scale=post, algo=algo, stream=stream)
+                                      post_scale=post, algo=algo, arrived=arrived,
+                                      elide=not case.get("no_elide", False), stream=stream)
                 stream.synchronize()
                 ms = (time.perf_counter() - t0) * 1e3
             if case.get("skew"):
@@ -145,7 +151,14 @@ def run_cases(rank: int, world: int, device: int, path: str, cases: List[dict],
             comm.status()
             got = from_torch(y, dout)
             exact = bits_equal(got, want, dout)
-            res = dict(case=case, exact=bool(exact), ms=ms, rank=rank)
+            res = dict(case=case, exact=bool(exact), ms=ms, rank=rank, kernel=comm.last_algo())
+            if case.get("expect_kernel") and res["kernel"] != case["expect_kernel"] and \
+                    not (case["expect_kernel"] == "nvls_inplace" and not caps.multicast):
+                res["exact"] = False
+                res["note"] = "took %s, expected %s" % (res["kernel"], case["expect_kernel"])
+                res.update(max_ulp=-1, mismatch=-1, normwise=-1.0)
+                results.append(res)
+                continue
             if not exact:
                 ulp = ulp_distance(got, want, dout)
                 ulp = np.where(np.isnan(to_f32(got, dout)) & np.isnan(to_f32(want, dout)), 0, ulp)
@@ -163,6 +176,27 @@ def run_cases(rank: int, world: int, device: int, path: str, cases: List[dict],
     finally:
         comm.close()
     return results
+
+
+def _run_bcast(comm, case, rank, world, dev, stream, ci):
+    """tok_broadcast: every replica starts from its own seeded bytes, ends with the root's."""
+    import torch
+    root, nbytes = case["bcast"], case["count"]
+    src = [np.random.RandomState(7000 + 13 * ci + r).randint(0, 256, size=nbytes, dtype=np.uint8)
+           for r in range(world)]
+    with torch.cuda.stream(stream):
+        if case.get("symm"):
+            t = comm.symm_empty(nbytes, torch.uint8)
+        else:
+            t = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        t.copy_(torch.from_numpy(src[rank]).to(dev))
+        comm.broadcast(t, root, stream=stream)
+        stream.synchronize()
+    comm.status()
+    got = t.cpu().numpy()
+    exact = bool(np.array_equal(got, src[root]))
+    return dict(case=case, exact=exact, rank=rank, ms=0.0, kernel=comm.last_algo(),
+                max_ulp=0 if exact else -1, mismatch=int((got != src[root]).sum()), normwise=0.0)
 
 
 def _proc_entry(rank, world, device, path, cases, job, env, q):

@@ -33,9 +33,44 @@ def assert_all_exact(results, expect_cases, world):
 
 
 def test_world1_local_kernel(tok_lib):
+    """world 1 = the fused scale/cast alone: the LDG.128 wave for every dtype triple, and the
+    cp.async.bulk (TMA) variant for the one-dtype cases (algo 7) incl. ragged tails and sizes that are
+    not a whole number of 16 KiB tiles."""
     cases = harness.standard_cases(1, algos=(0,), quick=False)
+    seed = 4000
+    for dt in ("bf16", "f32", "f16"):
+        for n in (1, 7, 8, 9, 4097, 8192, 65536 + 3, (1 << 20) + 5, 3 * (1 << 20) + 8):
+            for post in (False, True):
+                seed += 1
+                cases.append(dict(count=n, **{"in": dt, "wire": dt, "out": dt}, algo=7, seed=seed,
+                                  scale=1.0 / 3.0, post=post, pattern="wide",
+                                  inplace=(seed % 2 == 0), expect_kernel="local_tma"))
     res = harness.launch(1, cases, devices=[0], mode="thread", timeout=300)
     assert_all_exact(res, len(cases), 1)
+
+
+def test_world1_identity_bucket_is_elided(tok_lib):
+    """in == out, one dtype, scale 1 at world 1 is already the answer: no launch, no HBM pass — unless
+    the caller insists (TOK_FLAG_NO_ELIDE), in which case the kernel runs and changes nothing."""
+    import tempfile
+    import torch
+    from torch_on_k8s_b200.comm import Communicator
+    comm = Communicator("elide", 0, 1, 0, rendezvous_path=os.path.join(tempfile.mkdtemp(), "r"))
+    try:
+        x = torch.randn(1 << 20, device="cuda").to(torch.bfloat16)
+        ref = x.clone()
+        comm.allreduce_bucket(x, x, scale=1.0)
+        st = comm.stats()
+        assert (st.launches, st.elided) == (0, 1)
+        comm.allreduce_bucket(x, x, scale=1.0, elide=False)
+        torch.cuda.synchronize()
+        st = comm.stats()
+        assert (st.launches, st.elided) == (1, 1) and torch.equal(x, ref)
+        comm.allreduce_bucket(x, x, scale=0.5)           # real work is never elided
+        torch.cuda.synchronize()
+        assert comm.stats().launches == 2 and torch.equal(x, (ref.float() * 0.5).to(torch.bfloat16))
+    finally:
+        comm.close()
 
 
 @pytest.mark.parametrize("world", [2, 3, 4, 8])
@@ -94,6 +129,7 @@ def test_golden_gloo_vectors(tok_lib, n_gpus):
     import torch
     from oracle import allreduce_oracle as O
     from torch_on_k8s_b200.comm import Communicator
+    from torch_on_k8s_b200.elastic_dp import symm_tensor
     gold_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
     import tempfile
     import threading
@@ -103,7 +139,7 @@ def test_golden_gloo_vectors(tok_lib, n_gpus):
         devs, env = devices_for(world, n_gpus)
         os.environ.update(env or SHARED_ENV)
         path = os.path.join(tempfile.mkdtemp(prefix="tok8s-gold-"), "r")
-        outs, errs = {}, []
+        outs, zouts, errs = {}, {}, []
 
         def body(r):
             try:
@@ -112,12 +148,24 @@ def test_golden_gloo_vectors(tok_lib, n_gpus):
                 st = torch.cuda.Stream(device=devs[r])
                 with torch.cuda.stream(st):
                     x = torch.from_numpy(g["randn_x32_r%d" % r].copy()).to("cuda:%d" % devs[r])
-                    comm.allreduce_bucket(x, x, scale=1.0 / world, stream=st)
                     xb = harness.to_torch(g["randn_xb_r%d" % r], "bf16", "cuda:%d" % devs[r])
+                    # the zero-copy path DDP's buckets take: same inputs, in the symmetric pool
+                    n32 = (x.numel() // 4) * 4
+                    nb = (xb.numel() // 8) * 8
+                    # (direct pool allocation: a MemPool serves one communicator per process, and
+                    # these replicas are threads of one process)
+                    zx = symm_tensor(comm, n32, torch.float32).copy_(x[:n32])
+                    zb = symm_tensor(comm, nb, torch.bfloat16).copy_(xb[:nb])
+                    comm.allreduce_bucket(x, x, scale=1.0 / world, stream=st)
                     comm.allreduce_bucket(xb, xb, scale=1.0 / world, stream=st)
+                    comm.allreduce_bucket(zx, zx, scale=1.0 / world, stream=st)
+                    kz = comm.last_algo()
+                    comm.allreduce_bucket(zb, zb, scale=1.0 / world, stream=st)
                     st.synchronize()
                 comm.status()
+                assert kz in ("two_shot_inplace", "nvls_inplace"), kz
                 outs[r] = (x.cpu().numpy(), harness.from_torch(xb, "bf16"))
+                zouts[r] = (zx.cpu().numpy(), harness.from_torch(zb, "bf16"), kz)
                 comm.close()
             except Exception as e:  # noqa: BLE001
                 errs.append(repr(e))
@@ -137,13 +185,27 @@ def test_golden_gloo_vectors(tok_lib, n_gpus):
             ulp = O.ulp_distance(gotb, wantb, "bf16")
             assert ulp.max() <= 1 and (ulp != 0).mean() < 0.01, (world, r)
             assert np.array_equal(outs[0][0].view(np.uint32), got32.view(np.uint32))
+            # zero-copy: the P2P in-place kernel is the staged result bit for bit; the in-switch sum
+            # (NVLS, one GPU per replica) is held to the gloo goldens by the north_star tolerance
+            z32, zb, kz = zouts[r]
+            n32, nb = z32.size, zb.size
+            if kz == "two_shot_inplace":
+                assert np.array_equal(z32.view(np.uint32), got32[:n32].view(np.uint32)), (world, r)
+                assert np.array_equal(zb, gotb[:nb]), (world, r)
+            errz = np.abs(z32.astype(np.float64) - want[:n32].astype(np.float64)).max()
+            assert errz / np.abs(want).max() <= 1e-5, (world, r, kz)
+            ulpz = O.ulp_distance(zb, wantb[:nb], "bf16")
+            assert ulpz.max() <= 1, (world, r, kz)
 
 
 @pytest.mark.parametrize("world", [2, 3, 4])
 def test_zero_copy_symmetric_pool(tok_lib, n_gpus, world):
     """Buckets allocated in the symmetric pool (torch.cuda.MemPool over tok_pool_malloc) are
-    exchanged in place by the peer-memory kernel — bit-exact vs the oracle with the scale applied to
-    the sum — and an asymmetric allocation is detected in-kernel instead of corrupting gradients."""
+    exchanged in place: 1-warp arrival + the P2P in-place kernel (reduce own sub-slab from every
+    replica's bucket, push the result into every replica's bucket).  PRE and POST scaling are
+    bit-exact vs the oracle at every world size (1/3 is not a power of two); the split
+    arrive-then-exchange form gives the same bits; AUTO never picks a kernel that would change the
+    function; an asymmetric allocation is detected by the arrival instead of corrupting gradients."""
     devs, env = devices_for(world, n_gpus)
     cases = []
     seed = 700
@@ -151,16 +213,89 @@ def test_zero_copy_symmetric_pool(tok_lib, n_gpus, world):
         for n in (8, 4096, 65536 + 8, (1 << 20) + 64, 5 * (1 << 20)):
             seed += 1
             cases.append(dict(count=n, **{"in": dt, "wire": dt, "out": dt}, algo=3, seed=seed,
-                              scale=1.0 / world, symm=True))
+                              scale=1.0 / world, symm=True, split=(seed % 2 == 0),
+                              pattern="wide" if seed % 3 == 0 else "randn",
+                              expect_kernel="two_shot_inplace"))
+        seed += 1
+        cases.append(dict(count=(1 << 18) + 8, **{"in": dt, "wire": dt, "out": dt}, algo=3, seed=seed,
+                          scale=1.0 / 3.0, post=True, symm=True, pattern="wide",
+                          expect_kernel="two_shot_inplace"))
+        seed += 1   # AUTO + PRE with a factor that is not a power of two must stay on the exact kernel
+        cases.append(dict(count=(9 << 20) // 2, **{"in": dt, "wire": dt, "out": dt}, algo=0, seed=seed,
+                          scale=1.0 / 3.0, symm=True, split=True, expect_kernel="two_shot_inplace"))
     # not a whole number of 16-byte packs -> staged path, still correct
     cases.append(dict(count=65536 + 3, **{"in": "bf16", "wire": "bf16", "out": "bf16"}, algo=3,
-                      seed=799, scale=1.0 / world, symm=True))
+                      seed=799, scale=1.0 / world, symm=True, expect_kernel="two_shot"))
     cases.append(dict(count=1 << 20, **{"in": "bf16", "wire": "bf16", "out": "bf16"}, algo=3,
                       seed=800, scale=1.0 / world, symm=True, skew=True))
     res = harness.launch(world, cases, devices=devs, mode="proc", timeout=600, env=env)
     s = harness.summarize(res)
     assert s["bad"] == 0, s["worst"]
     assert s["total"] == len(cases) * world, (s["total"], [len(v) for v in res.values()])
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_broadcast_bit_exact(tok_lib, n_gpus, world):
+    """tok_broadcast (row f2): the root's bytes on every replica, for buffers in the symmetric pool
+    (multicast push when a multicast object is bound, else pulled from the root) and anywhere else
+    (through the root's staging buffer, chunked when larger than it), any root, ragged byte counts."""
+    devs, env = devices_for(world, n_gpus)
+    env = dict(env or {}, TOK_STAGING_MB="4")
+    cases = []
+    for i, n in enumerate((1, 15, 16, 4097, (1 << 20) + 3, (9 << 20) + 5)):
+        cases.append(dict(count=n, bcast=i % world, **{"in": "u8", "wire": "u8", "out": "u8"}))
+    for i, n in enumerate((16, 4096, (1 << 20) + 16, 6 << 20)):
+        cases.append(dict(count=n, bcast=(i + 1) % world, symm=True,
+                          **{"in": "u8", "wire": "u8", "out": "u8"}))
+    res = harness.launch(world, cases, devices=devs, mode="proc", timeout=600, env=env)
+    s = harness.summarize(res)
+    assert s["bad"] == 0, s["worst"]
+    assert s["total"] == len(cases) * world
+    kernels = {r["kernel"] for r in res[0] if "kernel" in r}
+    assert "bcast_staged" in kernels and ({"bcast_pull", "bcast_mc_push"} & kernels), kernels
+
+
+def test_symmetric_pool_recycles_released_segments(tok_lib):
+    """tok_pool_free is a real free: a released segment is handed out again (first fit, neighbours
+    merged, the top of the pool shrinks back) — DDP's bucket rebuild after iteration 1 and a re-wrap
+    after an elastic re-form do not leak the pool."""
+    import tempfile
+    import torch
+    from torch_on_k8s_b200 import _ffi
+    from torch_on_k8s_b200.comm import Communicator
+    os.environ["TOK_SYMM_POOL_MB"] = "64"
+    comm = Communicator("pool", 0, 1, 0, rendezvous_path=os.path.join(tempfile.mkdtemp(), "r"))
+    try:
+        import ctypes as C
+        L = _ffi.lib()
+
+        def alloc(mb):
+            p = C.c_void_p()
+            _ffi.check(L.tok_comm_symm_alloc(comm._h, mb << 20, C.byref(p)))
+            return p.value
+
+        base, size, used = comm.symm_info()
+        a, b, c = alloc(8), alloc(8), alloc(8)
+        assert (a, b, c) == (base, base + (8 << 20), base + (16 << 20))
+        _ffi.check(L.tok_comm_symm_free(comm._h, C.c_void_p(a), 8 << 20))
+        _ffi.check(L.tok_comm_symm_free(comm._h, C.c_void_p(b), 8 << 20))   # merges with a
+        assert comm.symm_info()[2] == 8 << 20
+        assert alloc(12) == base                       # first fit in the merged 16 MiB hole
+        assert alloc(4) == base + (12 << 20)
+        _ffi.check(L.tok_comm_symm_free(comm._h, C.c_void_p(c), 8 << 20))   # top shrinks back
+        assert alloc(2) == base + (16 << 20)
+        assert L.tok_comm_symm_free(comm._h, C.c_void_p(base + (40 << 20)), 2 << 20) != 0
+        # through torch: a MemPool tensor that is dropped gives its segment back
+        for _ in range(40):                            # 40 x 8 MiB through a 64 MiB pool
+            t = comm.symm_empty(8 << 20, torch.uint8)
+            assert comm.in_symmetric_pool(t)
+            del t
+            comm.mem_pool()                            # keep the pool object alive
+            torch.cuda.synchronize()
+            torch.cuda.memory.empty_cache()
+    finally:
+        comm.close()
+        os.environ["TOK_SYMM_POOL_MB"] = SHARED_ENV["TOK_SYMM_POOL_MB"]
 
 
 def test_nvls_tolerance(tok_lib, n_gpus):
@@ -179,11 +314,33 @@ def test_nvls_tolerance(tok_lib, n_gpus):
     for dt in ("bf16", "f32"):   # zero-copy NVLS: in-switch reduce straight on the pool buckets
         for n in (4096, (1 << 20) + 64, 5 * (1 << 20)):
             cases.append(dict(count=n, **{"in": dt, "wire": dt, "out": dt}, algo=4, seed=600 + n % 89,
-                              scale=1.0 / world, symm=True))
+                              scale=1.0 / world, symm=True, split=(n == 4096),
+                              expect_kernel="nvls_inplace"))
+    # what DDP's buckets take in bench.py: AUTO on pool buckets of the real ResNet-50 sizes, 1/N PRE
+    pow2 = world & (world - 1) == 0
+    auto_kernel = "nvls_inplace" if (world >= 3 and pow2) else "two_shot_inplace"
+    exact_ids = set()
+    for i, nbytes in enumerate((28256208, 22857856)):
+        cases.append(dict(count=nbytes // 2, **{"in": "bf16", "wire": "bf16", "out": "bf16"}, algo=0,
+                          seed=660 + i, scale=1.0 / world, symm=True, split=True,
+                          expect_kernel=auto_kernel))
+        # exactly representable data: any summation order gives the same bits, NVLS included
+        cases.append(dict(count=nbytes // 2, **{"in": "bf16", "wire": "bf16", "out": "bf16"}, algo=0,
+                          seed=670 + i, scale=1.0 / world if pow2 else 1.0, symm=True, split=True,
+                          pattern="ints", expect_kernel=auto_kernel if pow2 else None))
+        exact_ids.add(670 + i)
+    # f16 PRE buckets never take the in-switch sum (it could overflow before the 1/N)
+    cases.append(dict(count=1 << 20, **{"in": "f16", "wire": "f16", "out": "f16"}, algo=0, seed=690,
+                      scale=1.0 / world, symm=True, expect_kernel="two_shot_inplace"))
     res = harness.launch(world, cases, devices=list(range(world)), mode="proc", timeout=600)
     for rank, rs in res.items():
         for r in rs:
-            if "case" not in r or "skipped" in r or r["exact"]:
+            if "case" not in r or "skipped" in r:
+                continue
+            assert "note" not in r, r
+            if r["case"]["seed"] in exact_ids:
+                assert r["exact"], r
+            if r["exact"]:
                 continue
             wire, out = r["case"]["wire"], r["case"]["out"]
             if wire == "f32":
@@ -194,9 +351,12 @@ def test_nvls_tolerance(tok_lib, n_gpus):
                 assert r["max_ulp"] <= per, r
 
 
-def test_dead_peer_times_out_instead_of_hanging(tok_lib):
-    """A replica whose peer never shows up at the in-kernel barrier gives up after
-    TOK_BARRIER_TIMEOUT_MS and reports TOK_ERR_TIMEOUT (a dead replica must not hang the GPU)."""
+@pytest.mark.parametrize("symm", [False, True])
+def test_dead_peer_times_out_instead_of_hanging(tok_lib, symm):
+    """A replica whose peer never shows up at the in-kernel barrier (staged bucket) or at the arrival
+    (zero-copy bucket) gives up after TOK_BARRIER_TIMEOUT_MS, reports TOK_ERR_TIMEOUT, and leaves NaN
+    in the bucket so that an optimizer cannot silently consume a half-exchanged gradient (a dead
+    replica must not hang the GPU)."""
     import tempfile
     import threading
     import torch
@@ -214,12 +374,16 @@ def test_dead_peer_times_out_instead_of_hanging(tok_lib):
     [t.start() for t in ts]
     [t.join(120) for t in ts]
     try:
-        x = torch.ones(4096, device="cuda")
+        from torch_on_k8s_b200.elastic_dp import symm_tensor
+        x = symm_tensor(comms[0], 4096, torch.float32).fill_(1.0) if symm else \
+            torch.ones(4096, device="cuda")
         comms[0].allreduce_bucket(x, x, scale=0.5)   # rank 1 never calls
         torch.cuda.synchronize()
         with pytest.raises(_ffi.TokError) as e:
             comms[0].status()
         assert e.value.code == _ffi.TOK_ERR_TIMEOUT
+        assert comms[0].last_algo() == ("two_shot_inplace" if symm else "one_shot")
+        assert bool(torch.isnan(x).all())
     finally:
         os.environ["TOK_BARRIER_TIMEOUT_MS"] = "60000"
         for c in comms.values():
@@ -342,7 +506,7 @@ def test_elastic_training_without_torch_distributed(tok_lib, n_gpus):
             edp = ElasticDataParallel(model, comm, algo=3)
             x, y = batch(i, 64)
             state[i] = dict(comm=comm, edp=edp, x=x.cuda(devs[i]), y=y.cuda(devs[i]), stream=st,
-                            opt=torch.optim.SGD(model.parameters(), lr=0.05))
+                            opt=torch.optim.SGD(model.parameters(), lr=0.05, momentum=0.9))
             st.synchronize()
 
     def step(ids, tag):
@@ -362,7 +526,7 @@ def test_elastic_training_without_torch_distributed(tok_lib, n_gpus):
         world = len(ids)
         for k in range(len(post[(tag, ids[0])])):
             want = O.allreduce_oracle([pre[(tag, i)][k] for i in ids], "f32", "f32", "f32",
-                                      1.0 / world, post=True)
+                                      1.0 / world)
             for i in ids:
                 assert np.array_equal(post[(tag, i)][k].view(np.uint32), want.view(np.uint32)), (tag, i, k)
         flat = {i: torch.cat([p.detach().flatten() for p in state[i]["edp"].module.parameters()]).cpu()
@@ -381,9 +545,17 @@ def test_elastic_training_without_torch_distributed(tok_lib, n_gpus):
         else:
             make(i, i, 4, 1)
     run_all(grow, [0, 1, 2, 3])
-    run_all(lambda i: (state[i]["edp"].sync_params(root=0), state[i]["stream"].synchronize()), [0, 1, 2, 3])
+    # joiners receive parameters, buffers AND the optimizer's momentum: without the latter the
+    # replicas would apply the same averaged gradients with different momentum and drift apart
+    run_all(lambda i: (state[i]["edp"].sync_params(root=0),
+                       state[i]["edp"].sync_optimizer_state(state[i]["opt"], root=0),
+                       state[i]["stream"].synchronize()), [0, 1, 2, 3])
+    mom = {i: torch.cat([state[i]["opt"].state[p]["momentum_buffer"].flatten()
+                         for p in state[i]["edp"].module.parameters()]).cpu() for i in range(4)}
+    assert all(torch.equal(mom[0], mom[i]) for i in (1, 2, 3)) and float(mom[0].abs().sum()) > 0
     step([0, 1, 2, 3], "w4a")
     step([0, 1, 2, 3], "w4b")
+    step([0, 1, 2, 3], "w4c")   # still bit-identical three momentum steps after the join
 
     keep = [0, 2]
     for i in (1, 3):

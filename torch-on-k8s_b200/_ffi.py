@@ -27,9 +27,14 @@ TOK_ERR_STATE = -10
 
 TOK_F32, TOK_BF16, TOK_F16 = 0, 1, 2
 TOK_ALGO_AUTO, TOK_ALGO_LOCAL, TOK_ALGO_ONE_SHOT, TOK_ALGO_TWO_SHOT, TOK_ALGO_NVLS = 0, 1, 2, 3, 4
-ALGO_NAMES = {0: "auto", 1: "local", 2: "one_shot", 3: "two_shot", 4: "nvls"}
+TOK_ALGO_LOCAL_TMA = 7
+ALGO_NAMES = {0: "auto", 1: "local", 2: "one_shot", 3: "two_shot", 4: "nvls",
+              5: "two_shot_inplace", 6: "nvls_inplace", 7: "local_tma",
+              16: "bcast_mc_push", 17: "bcast_pull", 18: "bcast_staged"}
 TOK_FLAG_SCALE_POST = 0x1
 TOK_FLAG_NO_ZERO_COPY = 0x2
+TOK_FLAG_ARRIVED = 0x4
+TOK_FLAG_NO_ELIDE = 0x8
 TOK_FLAG_ALGO_SHIFT = 8
 TOK_MAX_WORLD = 8
 
@@ -70,6 +75,17 @@ class Caps(C.Structure):
     ]
 
 
+class Stats(C.Structure):
+    _fields_ = [
+        ("launches", C.c_uint64),
+        ("arrivals", C.c_uint64),
+        ("elided", C.c_uint64),
+        ("broadcasts", C.c_uint64),
+        ("last_algo", C.c_int),
+        ("last_ctas", C.c_int),
+    ]
+
+
 # Every symbol include/tok8s.h declares: name -> (restype, argtypes).  tests/test_abi.py checks the
 # header and this table against the built library.
 _P = C.c_void_p
@@ -87,6 +103,10 @@ PROTOTYPES = {
     "tok_comm_caps": (C.c_int, [_P, C.POINTER(Caps)]),
     "tok_allreduce_bucket": (C.c_int, [_P, _P, _P, C.c_size_t, C.c_int, C.c_int, C.c_int,
                                        C.c_float, C.c_uint, _P]),
+    "tok_bucket_arrive": (C.c_int, [_P, _P, C.c_size_t, C.c_int, C.c_float, C.c_uint, _P, _IP]),
+    "tok_broadcast": (C.c_int, [_P, _P, C.c_size_t, C.c_int, _P]),
+    "tok_comm_stats": (C.c_int, [_P, C.POINTER(Stats)]),
+    "tok_comm_symm_free": (C.c_int, [_P, _P, C.c_size_t]),
     "tok_allreduce_algo": (C.c_int, [_P, C.c_size_t, _IP]),
     "tok_comm_launches": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
     "tok_comm_symm_alloc": (C.c_int, [_P, C.c_size_t, _PP]),

@@ -13,8 +13,8 @@ from typing import Optional
 import torch
 
 from . import _ffi
-from ._ffi import (TOK_ALGO_AUTO, TOK_BF16, TOK_F16, TOK_F32, TOK_FLAG_ALGO_SHIFT,
-                   TOK_FLAG_SCALE_POST, Caps, TokError, check, lib)
+from ._ffi import (TOK_ALGO_AUTO, TOK_BF16, TOK_F16, TOK_F32, TOK_FLAG_ALGO_SHIFT, TOK_FLAG_ARRIVED,
+                   TOK_FLAG_NO_ELIDE, TOK_FLAG_SCALE_POST, Caps, Stats, TokError, check, lib)
 
 _DTYPES = {torch.float32: TOK_F32, torch.bfloat16: TOK_BF16, torch.float16: TOK_F16}
 
@@ -78,6 +78,15 @@ class Communicator:
         check(lib().tok_comm_launches(self._h, C.byref(n)))
         return n.value
 
+    def stats(self) -> Stats:
+        """launches / arrivals / elided / broadcasts so far + algorithm and grid of the last launch."""
+        st = Stats()
+        check(lib().tok_comm_stats(self._h, C.byref(st)))
+        return st
+
+    def last_algo(self) -> str:
+        return _ffi.ALGO_NAMES.get(self.stats().last_algo, "?")
+
     def status(self) -> None:
         check(lib().tok_comm_status(self._h))
 
@@ -85,9 +94,11 @@ class Communicator:
     def allreduce_bucket(self, inp: torch.Tensor, out: Optional[torch.Tensor] = None, *,
                          scale: float = 1.0, wire_dtype: Optional[torch.dtype] = None,
                          post_scale: bool = False, algo: int = TOK_ALGO_AUTO,
-                         zero_copy: bool = True,
+                         zero_copy: bool = True, arrived: bool = False, elide: bool = True,
                          stream: Optional[torch.cuda.Stream] = None) -> torch.Tensor:
-        """out = cast_out(sum over replicas of cast_wire(inp * scale)); stream-ordered, no sync."""
+        """out = cast_out(sum over replicas of cast_wire(inp * scale)); stream-ordered, no sync.
+        arrived: bucket_arrive() was already enqueued for this bucket on this stream.
+        elide=False: at world 1 launch the fused scale/cast even when it is an identity."""
         if out is None:
             out = inp
         if not inp.is_cuda or not out.is_cuda:
@@ -98,14 +109,43 @@ class Communicator:
         if inp.numel() != out.numel():
             raise TokError(_ffi.TOK_ERR_INVALID, "in/out element counts differ")
         wire = wire_dtype or inp.dtype
-        flags = (TOK_FLAG_SCALE_POST if post_scale else 0) | (algo << TOK_FLAG_ALGO_SHIFT) | \
-            (0 if zero_copy else _ffi.TOK_FLAG_NO_ZERO_COPY)
+        flags = self._flags(post_scale, algo, zero_copy) | (TOK_FLAG_ARRIVED if arrived else 0) | \
+            (0 if elide else TOK_FLAG_NO_ELIDE)
         s = stream if stream is not None else torch.cuda.current_stream(inp.device)
         check(lib().tok_allreduce_bucket(self._h, inp.data_ptr(), out.data_ptr(), inp.numel(),
                                          tok_dtype(inp.dtype), tok_dtype(wire),
                                          tok_dtype(out.dtype), float(scale), flags,
                                          C.c_void_p(s.cuda_stream)))
         return out
+
+    @staticmethod
+    def _flags(post_scale: bool, algo: int, zero_copy: bool) -> int:
+        return (TOK_FLAG_SCALE_POST if post_scale else 0) | (algo << TOK_FLAG_ALGO_SHIFT) | \
+            (0 if zero_copy else _ffi.TOK_FLAG_NO_ZERO_COPY)
+
+    def bucket_arrive(self, bucket: torch.Tensor, *, scale: float = 1.0, post_scale: bool = False,
+                      algo: int = TOK_ALGO_AUTO, zero_copy: bool = True,
+                      stream: Optional[torch.cuda.Stream] = None) -> bool:
+        """Enqueue the 1-warp arrival for a zero-copy bucket ("mine is ready", wait for every
+        peer's).  Returns True when the later allreduce_bucket(bucket, bucket, ...) — same scale /
+        flags — must be called with arrived=True; False when that call takes a staged kernel."""
+        s = stream if stream is not None else torch.cuda.current_stream(bucket.device)
+        got = C.c_int(0)
+        check(lib().tok_bucket_arrive(self._h, bucket.data_ptr(), bucket.numel(),
+                                      tok_dtype(bucket.dtype), float(scale),
+                                      self._flags(post_scale, algo, zero_copy),
+                                      C.c_void_p(s.cuda_stream), C.byref(got)))
+        return bool(got.value)
+
+    def broadcast(self, buf: torch.Tensor, root: int = 0,
+                  stream: Optional[torch.cuda.Stream] = None) -> torch.Tensor:
+        """Replicate replica `root`'s `buf` (any dtype, contiguous) into every replica's `buf`."""
+        if not buf.is_cuda or not buf.is_contiguous():
+            raise TokError(_ffi.TOK_ERR_INVALID, "broadcast needs a contiguous CUDA tensor")
+        s = stream if stream is not None else torch.cuda.current_stream(buf.device)
+        check(lib().tok_broadcast(self._h, buf.data_ptr(), buf.numel() * buf.element_size(), root,
+                                  C.c_void_p(s.cuda_stream)))
+        return buf
 
     # ---- symmetric pool (zero-copy buckets) ---------------------------------------------------
     def symm_info(self):

@@ -12,6 +12,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <errno.h>
+#include <math.h>
 #include <fcntl.h>
 #include <poll.h>
 #include <stdarg.h>
@@ -342,6 +343,7 @@ struct tok_comm {
   size_t cap_bytes = 0;
   size_t pool_bytes = 0;   // symmetric pool for zero-copy buckets
   size_t pool_used = 0;    // bump pointer (identical allocation sequence on every replica)
+  std::vector<std::pair<size_t, size_t>> pool_free;  // (offset, bytes) of released segments, by offset
   std::mutex pool_mu;      // tok_pool_malloc may be entered from any allocator-calling thread
   size_t heap_bytes = 0;
   bool zero_copy = true;
@@ -369,10 +371,17 @@ struct tok_comm {
   size_t nvls_min = 0;
   int force_algo = 0;
   bool disable_nvls = false;
-  unsigned long long barrier_timeout_ns = 20000ull * 1000000ull;
+  unsigned long long barrier_timeout_ns = 600000ull * 1000000ull;
   double rdzv_timeout_s = 120;
+  int local_tma = 0;        // world 1, one dtype: 1 = cp.async.bulk variant, 0 = LDG.128 wave
 
-  std::atomic<uint64_t> launches{0};
+  std::atomic<uint64_t> launches{0};    // exchange / broadcast / local kernels
+  std::atomic<uint64_t> arrivals{0};    // arrive kernels
+  std::atomic<uint64_t> elided{0};      // world-1 identity buckets that needed no launch
+  std::atomic<uint64_t> broadcasts{0};
+  std::atomic<int> last_algo{0};
+  std::atomic<int> last_ctas{0};
+  bool membership_dirty = false;  // exchange() got far enough to touch the peer mappings
 };
 
 static std::atomic<tok_comm*> g_pool_comm{nullptr};  // communicator behind tok_pool_malloc()
@@ -506,6 +515,7 @@ int alloc_local(tok_comm* c) {
 // scatters the full table back, then (re)builds the peer table and the multicast binding.
 int exchange(tok_comm* c) {
   Drv& d = drv();
+  c->membership_dirty = false;
   Star star;
   star.root = (c->rank == 0);
   star.world = c->world;
@@ -651,6 +661,7 @@ int exchange(tok_comm* c) {
   }
 
   // ---- build the peer table, reusing mappings of surviving peers (in-place re-form) -------------
+  c->membership_dirty = true;
   std::vector<PeerMap> next;
   int rc = TOK_OK;
   for (int r = 0; r < c->world && rc == TOK_OK; ++r) {
@@ -855,7 +866,10 @@ int create_impl(const char* job_id, int rank, int world, int max_world, int devi
   c->nvls_min = env_size("TOK_NVLS_MIN", 0);
   c->force_algo = static_cast<int>(env_size("TOK_ALGO", 0));
   c->disable_nvls = env_size("TOK_DISABLE_NVLS", 0) != 0;
-  c->barrier_timeout_ns = env_size("TOK_BARRIER_TIMEOUT_MS", 20000) * 1000000ull;
+  // NCCL's watchdog default is 600 s; replicas legitimately skew by tens of seconds (first-iteration
+  // cuDNN autotune, evaluation or a checkpoint on rank 0)
+  c->barrier_timeout_ns = env_size("TOK_BARRIER_TIMEOUT_MS", 600000) * 1000000ull;
+  c->local_tma = static_cast<int>(env_size("TOK_LOCAL_TMA", 0));
   c->rdzv_timeout_s = static_cast<double>(env_size("TOK_RDZV_TIMEOUT_S", 120));
 
   int rc = TOK_OK;
@@ -922,7 +936,7 @@ extern "C" {
 
 const char* tok_last_error(void) { return tok::last_error_cstr(); }
 
-const char* tok_version(void) { return "libtok8s 0.1 (sm_100a, abi 1)"; }
+const char* tok_version(void) { return "libtok8s 0.2 (sm_100a, abi 2)"; }
 
 void tok_free(void* p) { free(p); }
 
@@ -951,10 +965,21 @@ int tok_comm_reform(tok_comm_t* c, int new_world, int new_rank, uint64_t member_
                 (unsigned long long)member_mask, c->rank);
   DeviceGuard guard(c->device);
   RT_CHECK(cudaDeviceSynchronize());  // no collective of the old group may still be in flight
+  const int old_rank = c->rank, old_world = c->world;
+  const uint64_t old_epoch = c->epoch;
   c->rank = new_rank;
   c->world = new_world;
   c->epoch = epoch;
-  return exchange(c);
+  const int rc = exchange(c);
+  if (rc == TOK_ERR_RENDEZVOUS && !c->membership_dirty) {
+    // The membership exchange never completed (peers that were announced did not show up): nothing
+    // of the old group was unmapped yet, so the communicator stays usable with its previous
+    // membership and a later epoch (e.g. the controller's revert) can still be applied.
+    c->rank = old_rank;
+    c->world = old_world;
+    c->epoch = old_epoch;
+  }
+  return rc;
 }
 
 int tok_comm_abort(tok_comm_t* c) {
@@ -1036,24 +1061,77 @@ int tok_allreduce_algo(tok_comm_t* c, size_t wire_bytes, int* algo) {
 }
 
 // ---- symmetric pool ---------------------------------------------------------------------------
+// First-fit over the released segments (lowest offset first), else bump.  Deterministic: replicas
+// that perform the same allocate/release sequence get the same offsets — which is all the zero-copy
+// path needs, and the arrive kernel verifies it for every bucket.
+static size_t pool_base_off(const tok_comm* c) { return kFlagBytes + 2 * c->cap_bytes; }
+
 int tok_comm_symm_alloc(tok_comm_t* c, size_t bytes, void** ptr) {
   if (!c || !ptr) return fail(TOK_ERR_INVALID, "comm / ptr is null");
   const size_t need = round_up(std::max<size_t>(bytes, 1), 2u << 20);  // segment-friendly alignment
   std::lock_guard<std::mutex> lock(c->pool_mu);
+  char* base = reinterpret_cast<char*>(c->local_va) + pool_base_off(c);
+  for (size_t i = 0; i < c->pool_free.size(); ++i) {
+    auto& blk = c->pool_free[i];
+    if (blk.second < need) continue;
+    *ptr = base + blk.first;
+    if (blk.second == need) {
+      c->pool_free.erase(c->pool_free.begin() + static_cast<long>(i));
+    } else {
+      blk.first += need;
+      blk.second -= need;
+    }
+    return TOK_OK;
+  }
   if (c->pool_used + need > c->pool_bytes)
     return fail(TOK_ERR_INVALID,
                 "symmetric pool exhausted: %zu MiB used + %zu MiB requested > %zu MiB (TOK_SYMM_POOL_MB)",
                 c->pool_used >> 20, need >> 20, c->pool_bytes >> 20);
-  *ptr = reinterpret_cast<char*>(c->local_va) + kFlagBytes + 2 * c->cap_bytes + c->pool_used;
+  *ptr = base + c->pool_used;
   c->pool_used += need;
+  return TOK_OK;
+}
+
+int tok_comm_symm_free(tok_comm_t* c, void* ptr, size_t bytes) {
+  if (!c) return fail(TOK_ERR_INVALID, "comm is null");
+  if (!ptr) return TOK_OK;
+  const size_t size = round_up(std::max<size_t>(bytes, 1), 2u << 20);
+  std::lock_guard<std::mutex> lock(c->pool_mu);
+  const char* base = reinterpret_cast<const char*>(c->local_va) + pool_base_off(c);
+  const char* p = static_cast<const char*>(ptr);
+  if (p < base || p + size > base + c->pool_used || ((p - base) & ((2u << 20) - 1)))
+    return fail(TOK_ERR_INVALID, "pointer %p (+%zu) is not a live symmetric-pool segment", ptr, size);
+  const size_t off = static_cast<size_t>(p - base);
+  auto it = std::lower_bound(c->pool_free.begin(), c->pool_free.end(), std::make_pair(off, size_t{0}));
+  if ((it != c->pool_free.end() && it->first < off + size) ||
+      (it != c->pool_free.begin() && (it - 1)->first + (it - 1)->second > off))
+    return fail(TOK_ERR_STATE, "symmetric-pool segment at offset %zu released twice", off);
+  it = c->pool_free.insert(it, std::make_pair(off, size));
+  if (it + 1 != c->pool_free.end() && it->first + it->second == (it + 1)->first) {  // merge right
+    it->second += (it + 1)->second;
+    c->pool_free.erase(it + 1);
+  }
+  if (it != c->pool_free.begin() && (it - 1)->first + (it - 1)->second == it->first) {  // merge left
+    (it - 1)->second += it->second;
+    it = c->pool_free.erase(it) - 1;
+  }
+  if (it->first + it->second == c->pool_used) {  // the top of the pool shrinks back
+    c->pool_used = it->first;
+    c->pool_free.erase(it);
+  }
   return TOK_OK;
 }
 
 int tok_comm_symm_info(tok_comm_t* c, void** base, size_t* bytes, size_t* used) {
   if (!c) return fail(TOK_ERR_INVALID, "comm is null");
-  if (base) *base = reinterpret_cast<char*>(c->local_va) + kFlagBytes + 2 * c->cap_bytes;
+  if (base) *base = reinterpret_cast<char*>(c->local_va) + pool_base_off(c);
   if (bytes) *bytes = c->pool_bytes;
-  if (used) *used = c->pool_used;
+  if (used) {
+    std::lock_guard<std::mutex> lock(c->pool_mu);
+    size_t freed = 0;
+    for (auto& b : c->pool_free) freed += b.second;
+    *used = c->pool_used - freed;
+  }
   return TOK_OK;
 }
 
@@ -1063,8 +1141,8 @@ int tok_comm_use_as_pool(tok_comm_t* c) {
 }
 
 // torch.cuda.memory.CUDAPluggableAllocator entry points: segments of a torch.cuda.MemPool are carved
-// from the symmetric pool of the communicator selected with tok_comm_use_as_pool().  Freed segments
-// are not recycled (bump allocator): the pool is meant for long-lived gradient buckets.
+// from the symmetric pool of the communicator selected with tok_comm_use_as_pool() and go back to
+// its free list when torch releases them (DDP drops its first-generation buckets after iteration 1).
 void* tok_pool_malloc(ptrdiff_t size, int device, void* stream) {
   (void)stream;
   tok_comm* c = g_pool_comm.load();
@@ -1075,10 +1153,10 @@ void* tok_pool_malloc(ptrdiff_t size, int device, void* stream) {
 }
 
 void tok_pool_free(void* ptr, size_t size, int device, void* stream) {
-  (void)ptr;
-  (void)size;
-  (void)device;
   (void)stream;
+  tok_comm* c = g_pool_comm.load();
+  if (!c || device != c->device) return;  // communicator already gone: the heap went with it
+  tok_comm_symm_free(c, ptr, size);
 }
 
 int tok_comm_debug_read(tok_comm_t* c, uint64_t* out, size_t words) {
@@ -1092,79 +1170,203 @@ int tok_comm_debug_read(tok_comm_t* c, uint64_t* out, size_t words) {
 
 int tok_comm_launches(tok_comm_t* c, uint64_t* launches) {
   if (!c || !launches) return fail(TOK_ERR_INVALID, "comm / launches is null");
-  *launches = c->launches.load();
+  *launches = c->launches.load() + c->arrivals.load();
   return TOK_OK;
 }
 
-int tok_allreduce_bucket(tok_comm_t* c, const void* in, void* out, size_t count, int in_dtype,
-                         int wire_dtype, int out_dtype, float scale, unsigned flags,
-                         void* cuda_stream) {
-  if (!c) return fail(TOK_ERR_INVALID, "comm is null");
-  auto bad_dt = [](int d) { return d != TOK_F32 && d != TOK_BF16 && d != TOK_F16; };
-  if (bad_dt(in_dtype) || bad_dt(wire_dtype) || bad_dt(out_dtype))
-    return fail(TOK_ERR_INVALID, "unsupported dtype (in %d wire %d out %d)", in_dtype, wire_dtype,
-                out_dtype);
-  if (count == 0) return TOK_OK;
-  if (!in || !out) return fail(TOK_ERR_INVALID, "in / out is null");
-  if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(out) & 15))
-    return fail(TOK_ERR_ALIGN, "bucket pointers must be 16-byte aligned (in %p out %p)", in, out);
-  int st = tok_comm_status(c);
-  if (st != TOK_OK) return st;
+int tok_comm_stats(tok_comm_t* c, tok_stats_t* st) {
+  if (!c || !st) return fail(TOK_ERR_INVALID, "comm / stats is null");
+  memset(st, 0, sizeof(*st));
+  st->launches = c->launches.load();
+  st->arrivals = c->arrivals.load();
+  st->elided = c->elided.load();
+  st->broadcasts = c->broadcasts.load();
+  st->last_algo = c->last_algo.load();
+  st->last_ctas = c->last_ctas.load();
+  return TOK_OK;
+}
 
-  const int P = pack_elems(in_dtype, wire_dtype, out_dtype);
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// planning: which kernel a bucket takes
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+bool is_pow2_scale(float s) {
+  int e = 0;
+  return s > 0.f && frexpf(s, &e) == 0.5f;
+}
+
+struct Plan {
+  int algo = 0;          // TOK_ALGO_* or an internal id
+  bool inplace = false;  // zero-copy (preceded by an arrival)
+  size_t buf_off = 0;
+  bool elide = false;
+};
+
+void fill_common(const tok_comm* c, KArgs* a) {
+  memset(a, 0, sizeof(*a));
+  a->stage_off[0] = kFlagBytes;
+  a->stage_off[1] = kFlagBytes + c->cap_bytes;
+  a->slot_bytes = c->cap_bytes / kMaxWorld;
+  for (int r = 0; r < kMaxWorld; ++r) a->peer[r] = c->peer[r];
+  a->mc = reinterpret_cast<char*>(c->mc_va);
+  a->ctr = c->ctr;
+  a->hostctl = c->hostctl_dev;
+  a->timeout_ns = c->barrier_timeout_ns;
+  a->dbg = c->dbg;
+  a->rank = c->rank;
+  a->world = c->world;
+}
+
+bool in_pool(const tok_comm* c, const void* p, size_t bytes) {
+  const char* lo = reinterpret_cast<const char*>(c->local_va) + kFlagBytes + 2 * c->cap_bytes;
+  const char* q = static_cast<const char*>(p);
+  return q >= lo && q + bytes <= lo + c->pool_bytes;
+}
+
+int plan_bucket(const tok_comm* c, const void* in, const void* out, size_t count, int in_dtype,
+                int wire_dtype, int out_dtype, float scale, unsigned flags, Plan* pl) {
   const size_t wsz = dtype_size(wire_dtype);
   const size_t isz = dtype_size(in_dtype);
-  const size_t osz = dtype_size(out_dtype);
+  const bool same_dt = in_dtype == wire_dtype && wire_dtype == out_dtype;
   int algo = static_cast<int>((flags & TOK_FLAG_ALGO_MASK) >> TOK_FLAG_ALGO_SHIFT);
+  const bool forced = algo != TOK_ALGO_AUTO;
   if (algo == TOK_ALGO_AUTO) algo = pick_algo(c, count * wsz);
-  if (algo < TOK_ALGO_LOCAL || algo > TOK_ALGO_NVLS)
+  if (algo == TOK_ALGO_LOCAL_TMA) {
+    if (c->world != 1 || !same_dt)
+      return fail(TOK_ERR_INVALID, "TOK_ALGO_LOCAL_TMA needs world == 1 and one dtype");
+    algo = kAlgoLocalTma;
+  } else if (algo < TOK_ALGO_LOCAL || algo > TOK_ALGO_NVLS) {
     return fail(TOK_ERR_INVALID, "unknown algorithm %d", algo);
-  if (algo == TOK_ALGO_LOCAL && c->world != 1)
+  }
+  if ((algo == TOK_ALGO_LOCAL || algo == kAlgoLocalTma) && c->world != 1)
     return fail(TOK_ERR_INVALID, "TOK_ALGO_LOCAL is only valid for world == 1 (world is %d)",
                 c->world);
   if (algo == TOK_ALGO_NVLS && !c->mc_va)
     return fail(TOK_ERR_UNSUPPORTED,
                 "NVLS requested but no multicast object is bound for this group");
-
+  if (c->world == 1) {
+    // a bucket that is already what the caller asked for needs no pass over HBM at all
+    pl->elide = !forced && in == out && same_dt && scale == 1.0f && !(flags & TOK_FLAG_NO_ELIDE);
+    if (algo == TOK_ALGO_LOCAL && !forced && same_dt && c->local_tma &&
+        count * wsz >= (1u << 20))
+      algo = kAlgoLocalTma;
+    pl->algo = algo;
+    return TOK_OK;
+  }
   // Zero-copy: the bucket lives in the symmetric pool (same offset on every replica), is exchanged
   // in place, in its own dtype, in whole 16-byte packs -> peers read / multicast it directly.
-  const char* pool_lo = reinterpret_cast<const char*>(c->local_va) + kFlagBytes + 2 * c->cap_bytes;
-  const char* pin = static_cast<const char*>(in);
-  const bool forced = (flags & TOK_FLAG_ALGO_MASK) != 0;
-  const bool in_pool = pin >= pool_lo && pin + count * isz <= pool_lo + c->pool_bytes;
-  bool inplace = c->zero_copy && !(flags & TOK_FLAG_NO_ZERO_COPY) && c->world > 1 && in == out &&
-                 in_dtype == wire_dtype && wire_dtype == out_dtype && in_pool &&
-                 (count * wsz) % 16 == 0 && (algo == TOK_ALGO_TWO_SHOT || algo == TOK_ALGO_NVLS);
-  if (inplace && !forced && algo == TOK_ALGO_TWO_SHOT && c->mc_va && c->world >= 3)
-    algo = TOK_ALGO_NVLS;
-  size_t buf_off = 0;
+  bool inplace = c->zero_copy && !(flags & TOK_FLAG_NO_ZERO_COPY) && in == out && same_dt &&
+                 in_pool(c, in, count * isz) && (count * wsz) % 16 == 0 &&
+                 (algo == TOK_ALGO_TWO_SHOT || algo == TOK_ALGO_NVLS);
   if (inplace) {
-    buf_off = static_cast<size_t>(pin - reinterpret_cast<const char*>(c->local_va));
+    // The switch can only scale the SUM.  That equals the specified PRE semantics (scale every
+    // contribution, then sum) when the caller asked for POST or the factor is a power of two; a
+    // 16-bit float sum may also overflow before the 1/N is applied.  Everything else takes the P2P
+    // in-place kernel, which applies PRE exactly as the staged path does.
+    const bool post = (flags & TOK_FLAG_SCALE_POST) != 0;
+    const bool nvls_exact = (post || is_pow2_scale(scale)) && (wire_dtype != TOK_F16 || post);
+    if (!forced && algo == TOK_ALGO_TWO_SHOT && c->mc_va && c->world >= 3) algo = TOK_ALGO_NVLS;
+    if (algo == TOK_ALGO_NVLS && !nvls_exact) {
+      if (forced)
+        inplace = false;  // honour the forced algorithm through the staged kernel
+      else
+        algo = TOK_ALGO_TWO_SHOT;
+    }
+  }
+  if (inplace) {
+    pl->buf_off = static_cast<size_t>(static_cast<const char*>(in) -
+                                      reinterpret_cast<const char*>(c->local_va));
     algo = (algo == TOK_ALGO_NVLS) ? kAlgoNvlsInplace : kAlgoTwoShotInplace;
   }
+  pl->inplace = inplace;
+  pl->algo = algo;
+  return TOK_OK;
+}
+
+int check_bucket_args(tok_comm* c, const void* in, const void* out, int in_dtype, int wire_dtype,
+                      int out_dtype) {
+  if (!c) return fail(TOK_ERR_INVALID, "comm is null");
+  auto bad_dt = [](int d) { return d != TOK_F32 && d != TOK_BF16 && d != TOK_F16; };
+  if (bad_dt(in_dtype) || bad_dt(wire_dtype) || bad_dt(out_dtype))
+    return fail(TOK_ERR_INVALID, "unsupported dtype (in %d wire %d out %d)", in_dtype, wire_dtype,
+                out_dtype);
+  if (!in || !out) return fail(TOK_ERR_INVALID, "in / out is null");
+  if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(out) & 15))
+    return fail(TOK_ERR_ALIGN, "bucket pointers must be 16-byte aligned (in %p out %p)", in, out);
+  return tok_comm_status(c);
+}
+
+int do_arrive(tok_comm* c, size_t buf_off, void* stream) {
+  KArgs a;
+  fill_common(c, &a);
+  a.buf_off = buf_off;
+  int e = launch_arrive(a, stream);
+  if (e != 0)
+    return fail(TOK_ERR_CUDA, "arrive kernel launch failed: %s",
+                cudaGetErrorString(static_cast<cudaError_t>(e)));
+  c->arrivals.fetch_add(1);
+  return TOK_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int tok_bucket_arrive(tok_comm_t* c, const void* bucket, size_t count, int dtype, float scale,
+                      unsigned flags, void* cuda_stream, int* arrived) {
+  if (arrived) *arrived = 0;
+  if (count == 0) return TOK_OK;
+  int st = check_bucket_args(c, bucket, bucket, dtype, dtype, dtype);
+  if (st != TOK_OK) return st;
+  Plan pl;
+  st = plan_bucket(c, bucket, bucket, count, dtype, dtype, dtype, scale, flags, &pl);
+  if (st != TOK_OK) return st;
+  if (!pl.inplace) return TOK_OK;  // staged kernels carry their own barriers
+  DeviceGuard guard(c->device);
+  st = do_arrive(c, pl.buf_off, cuda_stream);
+  if (st == TOK_OK && arrived) *arrived = 1;
+  return st;
+}
+
+int tok_allreduce_bucket(tok_comm_t* c, const void* in, void* out, size_t count, int in_dtype,
+                         int wire_dtype, int out_dtype, float scale, unsigned flags,
+                         void* cuda_stream) {
+  if (c && count == 0) return TOK_OK;
+  int st = check_bucket_args(c, in, out, in_dtype, wire_dtype, out_dtype);
+  if (st != TOK_OK) return st;
+  Plan pl;
+  st = plan_bucket(c, in, out, count, in_dtype, wire_dtype, out_dtype, scale, flags, &pl);
+  if (st != TOK_OK) return st;
+  if (pl.elide) {
+    c->elided.fetch_add(1);
+    return TOK_OK;
+  }
+  const int algo = pl.algo;
+  const bool inplace = pl.inplace;
+  const int P = pack_elems(in_dtype, wire_dtype, out_dtype);
+  const size_t wsz = dtype_size(wire_dtype);
+  const size_t isz = dtype_size(in_dtype);
+  const size_t osz = dtype_size(out_dtype);
+  const bool local = algo == TOK_ALGO_LOCAL || algo == kAlgoLocalTma;
 
   // largest element count one launch may take (multiple of 8 elements -> 16-byte aligned chunks)
   size_t launch_cap = c->cap_bytes / wsz;
   if (algo == TOK_ALGO_ONE_SHOT) launch_cap = (c->cap_bytes / kMaxWorld) / wsz;
   launch_cap = launch_cap / (static_cast<size_t>(P) * kMaxWorld) * (static_cast<size_t>(P) * kMaxWorld);
-  if (algo == TOK_ALGO_LOCAL || inplace) launch_cap = (static_cast<size_t>(1) << 40);
+  if (local || inplace) launch_cap = (static_cast<size_t>(1) << 40);
 
   DeviceGuard guard(c->device);
+  if (inplace && !(flags & TOK_FLAG_ARRIVED)) {
+    st = do_arrive(c, pl.buf_off, cuda_stream);
+    if (st != TOK_OK) return st;
+  }
   KArgs a;
-  memset(&a, 0, sizeof(a));
-  a.stage_off[0] = kFlagBytes;
-  a.stage_off[1] = kFlagBytes + c->cap_bytes;
-  a.slot_bytes = c->cap_bytes / kMaxWorld;
-  for (int r = 0; r < kMaxWorld; ++r) a.peer[r] = c->peer[r];
-  a.mc = reinterpret_cast<char*>(c->mc_va);
-  a.ctr = c->ctr;
-  a.hostctl = c->hostctl_dev;
-  a.timeout_ns = c->barrier_timeout_ns;
-  a.dbg = c->dbg;
-  a.buf_off = buf_off;
+  fill_common(c, &a);
+  a.buf_off = pl.buf_off;
   a.scale = scale;
-  a.rank = c->rank;
-  a.world = c->world;
   a.flags = flags & TOK_FLAG_SCALE_POST;
 
   for (size_t off = 0; off < count; off += launch_cap) {
@@ -1175,8 +1377,15 @@ int tok_allreduce_bucket(tok_comm_t* c, const void* in, void* out, size_t count,
     a.total_packs = (n + P - 1) / P;
     int ctas;
     if (algo == TOK_ALGO_LOCAL) {
-      const size_t want = (a.total_packs + kThreads * 4 - 1) / (kThreads * 4);
-      ctas = static_cast<int>(std::min<size_t>(std::max<size_t>(want, 1), c->sm_count * 4));
+      // one even wave, at most 2 CTAs per SM, >= 8 packs per thread
+      const size_t full = n / P;
+      const size_t want = (full + kThreads * 8 - 1) / (kThreads * 8);
+      const size_t g = std::min<size_t>(std::max<size_t>(want, 1), static_cast<size_t>(c->sm_count) * 2);
+      a.packs_per_cta = (std::max<size_t>(full, 1) + g - 1) / g;
+      ctas = static_cast<int>(g);
+    } else if (algo == kAlgoLocalTma) {
+      const size_t tiles = (n / P * 16 + 16383) / 16384;
+      ctas = static_cast<int>(std::min<size_t>(std::max<size_t>(tiles, 1), static_cast<size_t>(c->sm_count) * 2));
       a.packs_per_cta = 0;
     } else {
       const size_t bytes = a.total_packs * P * wsz;
@@ -1198,7 +1407,7 @@ int tok_allreduce_bucket(tok_comm_t* c, const void* in, void* out, size_t count,
                                   cap_ctas);
       size_t L = (a.total_packs + g - 1) / g;
       if (algo != TOK_ALGO_ONE_SHOT) L = round_up(L, c->world);
-      if (inplace) a.buf_off = buf_off + off * isz;
+      if (inplace) a.buf_off = pl.buf_off + off * isz;
       a.packs_per_cta = L;
       ctas = static_cast<int>((a.total_packs + L - 1) / L);
     }
@@ -1207,7 +1416,68 @@ int tok_allreduce_bucket(tok_comm_t* c, const void* in, void* out, size_t count,
       return fail(TOK_ERR_CUDA, "allreduce kernel launch failed: %s",
                   cudaGetErrorString(static_cast<cudaError_t>(e)));
     c->launches.fetch_add(1);
+    c->last_algo.store(algo);
+    c->last_ctas.store(ctas);
   }
+  return TOK_OK;
+}
+
+int tok_broadcast(tok_comm_t* c, void* buf, size_t bytes, int root, void* cuda_stream) {
+  if (!c) return fail(TOK_ERR_INVALID, "comm is null");
+  if (root < 0 || root >= c->world)
+    return fail(TOK_ERR_INVALID, "broadcast root %d out of range (world %d)", root, c->world);
+  if (bytes == 0 || c->world == 1) return TOK_OK;
+  if (!buf) return fail(TOK_ERR_INVALID, "buf is null");
+  if (reinterpret_cast<uintptr_t>(buf) & 15)
+    return fail(TOK_ERR_ALIGN, "broadcast buffer must be 16-byte aligned (%p)", buf);
+  int st = tok_comm_status(c);
+  if (st != TOK_OK) return st;
+  DeviceGuard guard(c->device);
+  const bool pooled = c->zero_copy && in_pool(c, buf, bytes) && bytes % 16 == 0;
+  KArgs a;
+  fill_common(c, &a);
+  a.root = root;
+  auto grid = [&](size_t nbytes, KArgs* k) {
+    const size_t packs = std::max<size_t>(nbytes / 16, 1);
+    const size_t g = std::min<size_t>(std::max<size_t>((nbytes + c->cta_bytes - 1) / c->cta_bytes, 1), 64);
+    k->packs_per_cta = (packs + g - 1) / g;
+    return static_cast<int>((packs + k->packs_per_cta - 1) / k->packs_per_cta);
+  };
+  if (pooled) {
+    const size_t off = static_cast<size_t>(static_cast<char*>(buf) - reinterpret_cast<char*>(c->local_va));
+    st = do_arrive(c, off, cuda_stream);
+    if (st != TOK_OK) return st;
+    a.buf_off = off;
+    a.in = buf;
+    a.out = buf;
+    a.count = bytes;
+    const int mode = c->mc_va ? kBcastMcPush : kBcastPull;
+    const int ctas = grid(bytes, &a);
+    int e = launch_broadcast(mode, ctas, a, cuda_stream);
+    if (e != 0)
+      return fail(TOK_ERR_CUDA, "broadcast kernel launch failed: %s",
+                  cudaGetErrorString(static_cast<cudaError_t>(e)));
+    c->launches.fetch_add(1);
+    c->last_algo.store(mode);
+    c->last_ctas.store(ctas);
+  } else {
+    const size_t cap = c->cap_bytes;  // one staging buffer per launch
+    for (size_t off = 0; off < bytes; off += cap) {
+      const size_t n = std::min(cap, bytes - off);
+      a.in = static_cast<char*>(buf) + off;
+      a.out = static_cast<char*>(buf) + off;
+      a.count = n;
+      const int ctas = grid(n, &a);
+      int e = launch_broadcast(kBcastStaged, ctas, a, cuda_stream);
+      if (e != 0)
+        return fail(TOK_ERR_CUDA, "broadcast kernel launch failed: %s",
+                    cudaGetErrorString(static_cast<cudaError_t>(e)));
+      c->launches.fetch_add(1);
+      c->last_algo.store(kBcastStaged);
+      c->last_ctas.store(ctas);
+    }
+  }
+  c->broadcasts.fetch_add(1);
   return TOK_OK;
 }
 

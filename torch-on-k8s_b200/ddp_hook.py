@@ -26,13 +26,15 @@ class BucketAllreduceHook:
     """
 
     def __init__(self, comm: Communicator, *, wire_dtype: Optional[torch.dtype] = None,
-                 overlap: bool = True, record_events: bool = False, algo: int = 0):
+                 overlap: bool = True, record_events: bool = False, algo: int = 0,
+                 elide_identity: bool = True):
         self.comm = comm
         self.wire_dtype = wire_dtype
         self.overlap = overlap
         self.algo = algo
         self.record_events = record_events
-        self.events: List[Tuple[int, torch.cuda.Event, torch.cuda.Event]] = []
+        self.elide_identity = elide_identity   # world 1: skip the launch when it would be an identity
+        self.events: List[tuple] = []
         self._stream: Optional[torch.cuda.Stream] = None
         self.buckets_seen = 0
         self.zero_copy_buckets = 0   # buckets found inside the replica's symmetric pool
@@ -55,16 +57,26 @@ class BucketAllreduceHook:
             stream.wait_stream(cur)  # the bucket's gradients were produced on `cur`
         with torch.cuda.stream(stream):
             if self.record_events:
+                ea = torch.cuda.Event(enable_timing=True)
                 e0 = torch.cuda.Event(enable_timing=True)
                 e1 = torch.cuda.Event(enable_timing=True)
+                ea.record(stream)
+            # zero-copy buckets: the wait for the slowest replica's backward is a 1-warp arrival
+            # kernel; the exchange kernel behind it starts when every replica's bucket is ready
+            arrived = False
+            if world > 1 and self.wire_dtype in (None, buf.dtype):
+                arrived = self.comm.bucket_arrive(buf, scale=1.0 / world, algo=self.algo,
+                                                  stream=stream)
+            if self.record_events:
                 e0.record(stream)
             self.comm.allreduce_bucket(buf, buf, scale=1.0 / world, wire_dtype=self.wire_dtype,
-                                       algo=self.algo, stream=stream)
+                                       algo=self.algo, arrived=arrived,
+                                       elide=self.elide_identity, stream=stream)
             if self.record_events:
                 e1.record(stream)
                 wire = self.wire_dtype or buf.dtype
                 self.events.append((buf.numel() * torch.empty(0, dtype=wire).element_size(),
-                                    buf.numel() * buf.element_size(), e0, e1))
+                                    buf.numel() * buf.element_size(), ea, e0, e1))
             fut: torch.futures.Future = torch.futures.Future(devices=[buf.device])
             # Safe before the kernel finishes: the future records an event on the current (comm)
             # stream and consumers synchronise their streams with it (torch.futures.Future docs).
@@ -83,11 +95,13 @@ class BucketAllreduceHook:
         return tok8s_bucket_allreduce_hook
 
     def drain_events(self):
-        """[(wire_bytes, bucket_bytes, milliseconds)] of the recorded launches; clears the list."""
+        """[(wire_bytes, bucket_bytes, exchange_ms, arrival_wait_ms)] of the recorded buckets; clears
+        the list.  exchange_ms spans the exchange kernel alone, arrival_wait_ms the arrival kernel in
+        front of it (the wait for the slowest replica; 0 for staged buckets)."""
         out = []
-        for wire_bytes, bucket_bytes, e0, e1 in self.events:
+        for wire_bytes, bucket_bytes, ea, e0, e1 in self.events:
             e1.synchronize()
-            out.append((wire_bytes, bucket_bytes, e0.elapsed_time(e1)))
+            out.append((wire_bytes, bucket_bytes, e0.elapsed_time(e1), ea.elapsed_time(e0)))
         self.events = []
         return out
 

@@ -42,6 +42,39 @@ def symm_tensor(comm: Communicator, numel: int, dtype: torch.dtype) -> torch.Ten
     return raw[:nbytes].view(dtype)
 
 
+@torch.no_grad()
+def broadcast_coalesced(comm: Communicator, tensors, root: int = 0) -> None:
+    """Replicate `root`'s `tensors` (one dtype, same device) into every replica's, bit for bit: packed
+    into one flat buffer, one tok_broadcast, unpacked in place on the receivers.  The flat buffer is
+    taken from the symmetric pool when it fits — the root then feeds all receivers with ONE
+    multimem.st stream through the NVSwitch — and released again (same order on every replica)."""
+    n = sum(t.numel() for t in tensors)
+    if n == 0:
+        return
+    dtype, dev = tensors[0].dtype, tensors[0].device
+    esz = tensors[0].element_size()
+    n_pad = (n * esz + 15) // 16 * 16 // esz
+    ptr = C.c_void_p()
+    pooled = lib().tok_comm_symm_alloc(comm._h, n_pad * esz, C.byref(ptr)) == 0
+    if pooled:
+        raw = torch.as_tensor(_RawCuda(ptr.value, n_pad * esz), device=dev)
+        flat = raw.view(dtype)
+    else:
+        flat = torch.empty(n_pad, dtype=dtype, device=dev)
+    if comm.rank == root:
+        torch.cat([t.reshape(-1) for t in tensors], out=flat[:n])
+    comm.broadcast(flat, root)
+    if comm.rank != root:
+        off = 0
+        for t in tensors:
+            t.copy_(flat[off:off + t.numel()].view(t.shape))
+            off += t.numel()
+    if pooled:
+        torch.cuda.current_stream(dev).synchronize()   # the segment is recycled: nothing in flight
+        del flat, raw
+        check(lib().tok_comm_symm_free(comm._h, ptr, n_pad * esz))
+
+
 def bucket_assignment(sizes_bytes, keys, caps):
     """Gradient-bucket assignment of torch's Reducer (compute_bucket_assignment_by_size, reached from
     torch/nn/parallel/distributed.py:1183-1275 — SURVEY.md §8 row a10): walk the tensors in the given
@@ -101,31 +134,86 @@ class ElasticDataParallel(torch.nn.Module):
     def reduce_grads(self, stream: Optional[torch.cuda.Stream] = None) -> None:
         """Average the gradient buckets across the current peer group (in place, zero-copy)."""
         world = self.comm.world
-        for b in self.buckets:
-            self.comm.allreduce_bucket(b, b, scale=1.0 / world, post_scale=True, algo=self.algo,
-                                       stream=stream)
+        for b in self.buckets:   # PRE scale: the same function as built-in DDP at every world size
+            self.comm.allreduce_bucket(b, b, scale=1.0 / world, algo=self.algo, stream=stream)
 
     # ---- elastic ------------------------------------------------------------------------------
     def reform(self, new_world: int, new_rank: int, member_mask: int, epoch: int) -> None:
         self.comm.reform(new_world, new_rank, member_mask, epoch)
 
     @torch.no_grad()
-    def sync_params(self, root: int = 0) -> None:
-        """Replicate rank `root`'s parameters and buffers to the whole group through the exchange
-        kernels themselves (root contributes its values, everybody else zeros)."""
+    def _broadcast_tensors(self, tensors, root: int) -> None:
+        """Coalesced broadcast (dist._broadcast_coalesced's job, torch/nn/parallel/distributed.py:1032)
+        through tok_broadcast: tensors are packed per dtype into one flat buffer, replicated
+        bit-for-bit from `root`, and unpacked in place on the receivers."""
         me = self.comm.rank
-        tensors = [p.data for p in self.module.parameters()] + \
-                  [b for b in self.module.buffers() if b.is_floating_point()]
         by_dtype = {}
         for t in tensors:
             by_dtype.setdefault(t.dtype, []).append(t)
         for dtype, ts in by_dtype.items():
             n = sum(t.numel() for t in ts)
-            flat = torch.zeros((n + 7) // 8 * 8, dtype=dtype, device=ts[0].device)
-            if me == root:
-                torch.cat([t.reshape(-1) for t in ts], out=flat[:n])
-            self.comm.allreduce_bucket(flat, flat, scale=1.0)
-            off = 0
-            for t in ts:
-                t.copy_(flat[off:off + t.numel()].view(t.shape))
-                off += t.numel()
+            if n == 0:
+                continue
+            broadcast_coalesced(self.comm, ts, root)
+
+    @torch.no_grad()
+    def sync_params(self, root: int = 0) -> None:
+        """Replicate rank `root`'s parameters and ALL buffers (BatchNorm's integer
+        num_batches_tracked included) to the whole group — what a replica that joins at an elastic
+        re-form needs before its first step."""
+        self._broadcast_tensors([p.data for p in self.module.parameters()] +
+                                [b for b in self.module.buffers()], root)
+
+    @torch.no_grad()
+    def sync_optimizer_state(self, optimizer: torch.optim.Optimizer, root: int = 0) -> None:
+        """Replicate `root`'s optimizer state (SGD momentum buffers, Adam moments and step counts).
+        Without it a joiner would apply the same averaged gradients with different momentum and the
+        replicas would drift apart for good.  State is created lazily by torch optimizers, so which
+        entries exist is itself part of what must be replicated: the root announces its layout (one
+        small broadcast), everybody allocates missing entries, then the tensors follow."""
+        me = self.comm.rank
+        dev = next(self.module.parameters()).device
+        params = [p for g in optimizer.param_groups for p in g["params"]]
+        # layout = for every parameter, which tensor-valued state keys the root holds (bitmask over
+        # the sorted union of known keys; python scalars such as `step` ints travel as f64)
+        keys = ["momentum_buffer", "exp_avg", "exp_avg_sq", "max_exp_avg_sq", "step", "square_avg",
+                "acc_delta", "sum"]
+        layout = torch.zeros(len(params), dtype=torch.int64, device=dev)
+        if me == root:
+            for i, p in enumerate(params):
+                st = optimizer.state.get(p, {})
+                layout[i] = sum(1 << k for k, name in enumerate(keys) if st.get(name) is not None)
+        self.comm.broadcast(layout, root)
+        masks = layout.tolist()
+        tensors, scalars = [], []
+        for p, m in zip(params, masks):
+            st = optimizer.state[p] if m else optimizer.state.get(p, {})
+            for k, name in enumerate(keys):
+                if not (m >> k) & 1:
+                    if name in st and me != root:
+                        del st[name]
+                    continue
+                v = st.get(name)
+                if torch.is_tensor(v):
+                    if v.device != p.device and v.dim() == 0:   # host-side step counter
+                        scalars.append((st, name, v))
+                    else:
+                        tensors.append(v)
+                elif v is None:          # joiner: allocate what the root has
+                    if name == "step":
+                        st[name] = torch.zeros((), dtype=torch.float32)
+                        scalars.append((st, name, st[name]))
+                    else:
+                        st[name] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                        tensors.append(st[name])
+                else:                    # python number
+                    scalars.append((st, name, v))
+        self._broadcast_tensors(tensors, root)
+        if scalars:
+            flat = torch.tensor([float(v) for _, _, v in scalars], dtype=torch.float64, device=dev)
+            self.comm.broadcast(flat, root)
+            for (st, name, old), v in zip(scalars, flat.tolist()):
+                if torch.is_tensor(old):
+                    old.fill_(v)
+                else:
+                    st[name] = type(old)(v)

@@ -29,7 +29,8 @@ class Replica:
 
     def wrap(self, model: torch.nn.Module, *, bucket_cap_mb: int = 25,
              wire_dtype: Optional[torch.dtype] = None, overlap: bool = True,
-             record_events: bool = False, zero_copy: bool = True, **ddp_kwargs):
+             record_events: bool = False, zero_copy: bool = True, elide_identity: bool = True,
+             **ddp_kwargs):
         """DistributedDataParallel(model) whose gradient buckets go through libtok8s.
 
         zero_copy: allocate DDP's bucket storage inside this replica's symmetric pool (a
@@ -40,11 +41,15 @@ class Replica:
         from torch.nn.parallel import DistributedDataParallel as DDP
         scope = None
         if zero_copy and self.world > 1 and wire_dtype is None:
-            try:
-                self.comm.mem_pool()
-                scope = self.comm.symmetric
-            except Exception:  # noqa: BLE001 — MemPool unavailable: staged path
-                scope = None
+            # a MemPool that cannot be created is an error, not a reason to change kernels silently:
+            # pass zero_copy=False to ask for the staged path
+            self.comm.mem_pool()
+            scope = self.comm.symmetric
+        # DDP's own start-up broadcast (dist._broadcast_coalesced over the process group) is replaced
+        # by tok_broadcast: init_sync=False skips it, broadcast_module_states() does it over NVLink
+        ddp_kwargs.setdefault("init_sync", False)
+        if self.world > 1 and not ddp_kwargs["init_sync"]:
+            self.broadcast_module_states(model)
         if scope is None:
             ddp = DDP(model, device_ids=[self.device.index], bucket_cap_mb=bucket_cap_mb,
                       gradient_as_bucket_view=True, **ddp_kwargs)
@@ -61,9 +66,19 @@ class Replica:
                         return inner(*a, **k)
                 ddp._pre_forward = _pre_forward
         hook = BucketAllreduceHook(self.comm, wire_dtype=wire_dtype, overlap=overlap,
-                                   record_events=record_events)
+                                   record_events=record_events, elide_identity=elide_identity)
         ddp.register_comm_hook(None, hook.as_function())
         return ddp, hook
+
+    def broadcast_module_states(self, module: torch.nn.Module, root: int = 0) -> None:
+        """Rank `root`'s parameters and buffers to every replica (DDP's _sync_module_states,
+        torch/nn/parallel/distributed.py:1032, over tok_broadcast instead of the process group)."""
+        from .elastic_dp import broadcast_coalesced
+        by_dtype = {}
+        for t in list(module.parameters()) + list(module.buffers()):
+            by_dtype.setdefault(t.dtype, []).append(t.data)
+        for ts in by_dtype.values():
+            broadcast_coalesced(self.comm, ts, root)
 
     def poll_membership(self):
         """Elastic add/drop without a restart: read the membership epoch file the controller writes
