@@ -85,8 +85,10 @@ def bits_equal(a: np.ndarray, b: np.ndarray, dtype: str) -> bool:
 
 
 def run_cases(rank: int, world: int, device: int, path: str, cases: List[dict],
-              job: str = "harness") -> List[dict]:
-    """Body of one replica.  Returns one result dict per case."""
+              job: str = "harness", use_mempool: bool = True) -> List[dict]:
+    """Body of one replica.  Returns one result dict per case.  use_mempool: pool buckets come from a
+    torch.cuda.MemPool over tok_pool_malloc (one communicator per process) — replicas that are
+    threads of one process allocate from their pool directly instead."""
     import torch
     from oracle.allreduce_oracle import allreduce_f32_unrounded, allreduce_oracle, to_f32, ulp_distance
     from torch_on_k8s_b200.comm import Communicator
@@ -96,6 +98,14 @@ def run_cases(rank: int, world: int, device: int, path: str, cases: List[dict],
     comm = Communicator(job, rank, world, device, rendezvous_path=path)
     stream = torch.cuda.Stream(device=dev)
     results = []
+    if use_mempool:
+        symm_empty = comm.symm_empty
+    else:
+        from torch_on_k8s_b200.elastic_dp import symm_tensor
+
+        def symm_empty(n, dt):
+            return symm_tensor(comm, n, dt)
+    comm._test_symm_empty = symm_empty
     caps = comm.caps()
     try:
         for ci, case in enumerate(cases):
@@ -121,8 +131,8 @@ def run_cases(rank: int, world: int, device: int, path: str, cases: List[dict],
             with torch.cuda.stream(stream):
                 if symm:
                     if case.get("skew") and rank == world - 1:
-                        _extra = comm.symm_empty(count, torch_dtype(din))  # steals x's block
-                    x = comm.symm_empty(count, torch_dtype(din))
+                        _extra = symm_empty(count, torch_dtype(din))  # steals x's block
+                    x = symm_empty(count, torch_dtype(din))
                     x.copy_(to_torch(inputs[rank], din, dev))
                     assert comm.in_symmetric_pool(x)
                     y = x
@@ -186,7 +196,7 @@ def _run_bcast(comm, case, rank, world, dev, stream, ci):
            for r in range(world)]
     with torch.cuda.stream(stream):
         if case.get("symm"):
-            t = comm.symm_empty(nbytes, torch.uint8)
+            t = comm._test_symm_empty(nbytes, torch.uint8)
         else:
             t = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         t.copy_(torch.from_numpy(src[rank]).to(dev))
@@ -256,7 +266,7 @@ def launch(world: int, cases: List[dict], *, devices: Optional[List[int]] = None
 
         def body(r):
             try:
-                out[r] = run_cases(r, world, devices[r], path, cases, job)
+                out[r] = run_cases(r, world, devices[r], path, cases, job, use_mempool=False)
             except Exception:  # noqa: BLE001
                 errs.append((r, traceback.format_exc()))
 

@@ -38,6 +38,8 @@ class BucketAllreduceHook:
         self._stream: Optional[torch.cuda.Stream] = None
         self.buckets_seen = 0
         self.zero_copy_buckets = 0   # buckets found inside the replica's symmetric pool
+        self.last_step_bytes: List[int] = []   # wire bytes of the buckets of the last finished step
+        self._cur_step_bytes: List[int] = []
 
     def _comm_stream(self, device) -> torch.cuda.Stream:
         if self._stream is None:
@@ -82,6 +84,10 @@ class BucketAllreduceHook:
             # stream and consumers synchronise their streams with it (torch.futures.Future docs).
             fut.set_result(buf)
         self.buckets_seen += 1
+        wire_dt = self.wire_dtype or buf.dtype
+        self._cur_step_bytes.append(buf.numel() * torch.empty(0, dtype=wire_dt).element_size())
+        if bucket.is_last():
+            self.last_step_bytes, self._cur_step_bytes = self._cur_step_bytes, []
         if self.buckets_seen <= 64 and self.wire_dtype in (None, buf.dtype) and \
                 self.comm.in_symmetric_pool(buf):
             self.zero_copy_buckets += 1
