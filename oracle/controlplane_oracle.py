@@ -416,14 +416,20 @@ class Coordinator:
     def weight(self, q: List[dict]) -> int:
         return sum(u["task_types"] if self.weight_mode == "task_types" else u["replicas"] for u in q)
 
+    def quota_key(self, u: dict) -> str:
+        """usage / assumptions are kept under the quota object the hard limit came from: the tenant's
+        own, else the default "" (the whole box) shared by every tenant without one"""
+        return u["tenant"] if u["tenant"] in self.hard else ""
+
     def quota_ok(self, u: dict, now: float) -> bool:
-        hard = self.hard.get(u["tenant"], self.hard.get(""))
+        qk = self.quota_key(u)
+        hard = self.hard.get(qk)
         if hard is None:
             return True
-        used = self.used.get(u["tenant"], 0)
+        used = self.used.get(qk, 0)
         if used > hard:
             return False
-        a = self.assumed.setdefault(u["tenant"], {})
+        a = self.assumed.setdefault(qk, {})
         for k in [k for k, (s, ts) in a.items() if now - ts > 60.0 or k in self.settled]:
             del a[k]
         avail = max(0, hard - used - sum(s for s, _ in a.values()))
@@ -449,7 +455,7 @@ class Coordinator:
                 if self.tie(ties) == 0:
                     sel = i
         u = cands[sel][0]
-        self.assumed.setdefault(u["tenant"], {})[u["uid"]] = (u["slots"], now)
+        self.assumed.setdefault(self.quota_key(u), {})[u["uid"]] = (u["slots"], now)
         self.queues[tenant] = [e for e in self.queues[tenant] if e["uid"] != u["uid"]]
         return tenant, u["uid"]
 

@@ -158,9 +158,10 @@ def test_golden_gloo_vectors(tok_lib, n_gpus):
                     zb = symm_tensor(comm, nb, torch.bfloat16).copy_(xb[:nb])
                     comm.allreduce_bucket(x, x, scale=1.0 / world, stream=st)
                     comm.allreduce_bucket(xb, xb, scale=1.0 / world, stream=st)
-                    comm.allreduce_bucket(zx, zx, scale=1.0 / world, stream=st)
+                    # (two-shot asked for by name: AUTO would take one-shot for buckets this small)
+                    comm.allreduce_bucket(zx, zx, scale=1.0 / world, algo=3, stream=st)
                     kz = comm.last_algo()
-                    comm.allreduce_bucket(zb, zb, scale=1.0 / world, stream=st)
+                    comm.allreduce_bucket(zb, zb, scale=1.0 / world, algo=3, stream=st)
                     st.synchronize()
                 comm.status()
                 assert kz in ("two_shot_inplace", "nvls_inplace"), kz

@@ -214,3 +214,82 @@ def test_torchelastic_revert_scales_in_and_deletes_out_of_range_replica(tok_lib,
     assert ctl.jobs[uid].job.num_tasks("Worker") == 1 and len(ctl.free_gpus) == 3
     st = ctl.jobs[uid].job.status["elasticScalingStatues"]["Worker"]
     assert st["elasticCondition"] == "Stop" and st["curReplicas"] == 1 and st["lastReplicas"] == 2
+
+
+def test_scale_request_publishes_membership_only_when_every_replica_runs(tok_lib, tmp_path, monkeypatch):
+    """Row a7, user-driven: Controller.scale() edits Worker.numTasks on a running job; the reconcile
+    creates the replicas it has GPUs for.  With one GPU short the new membership is NOT announced
+    (survivors re-forming towards a Pending replica would block in the rendezvous); after scaling back
+    to a size that fits, the out-of-range replicas are deleted and nothing that equals the already
+    known membership is re-announced; a scale-out that fits is announced once, nobody restarts."""
+    monkeypatch.setenv("RUN_S", "8")
+    m = manifest("sc", free_port())
+    for tt in ("Master", "Worker"):
+        m["spec"]["torchTaskSpecs"][tt]["template"]["spec"]["containers"][0]["command"] = \
+            [sys.executable, os.path.join(HERE, "cpu_elastic_replica.py")]
+    ctl = Controller(num_gpus=3, rdzv_dir=str(tmp_path), log_dir=str(tmp_path / "logs"))
+    uid = ctl.submit(m)
+    import time
+    t0 = time.time()
+    while time.time() - t0 < 20 and ctl.jobs[uid].job.last_condition() != "Running":
+        ctl.tick()
+        time.sleep(0.05)
+    assert ctl.jobs[uid].job.last_condition() == "Running"
+    with pytest.raises(ValueError):
+        ctl.scale(uid, "Worker", 8)                       # 1 master + 8 workers > 8 replicas
+    assert ctl.scale(uid, "Worker", 3) == 1               # needs 4 GPUs, the box has 3
+    for _ in range(10):
+        ctl.tick()
+        time.sleep(0.05)
+    reps = ctl.jobs[uid].replicas["Worker"]
+    assert sorted(reps) == [0, 1, 2] and reps[2].proc is None and reps[2].phase == "Pending"
+    assert not [e for e in ctl.events if e[2] == "MembershipPublished"]
+    assert ctl.scale(uid, "Worker", 2) == 2               # fits: worker-2 (Pending) goes away
+    for _ in range(10):
+        ctl.tick()
+        time.sleep(0.05)
+    members = [json.loads(e[3]) for e in ctl.events if e[2] == "MembershipPublished"]
+    assert members == [{"epoch": 2, "world": 3, "survivor_mask": 0b011,
+                        "ranks": {"sc-master-0": 0, "sc-worker-0": 1, "sc-worker-1": 2}}]
+    assert ctl.scale(uid, "Worker", 1) == 3
+    res = ctl.run_until_done(timeout=60)
+    assert res[uid] == "Succeeded", ctl.events[-8:]
+    members = [json.loads(e[3]) for e in ctl.events if e[2] == "MembershipPublished"]
+    assert (members[-1]["epoch"], members[-1]["world"], members[-1]["survivor_mask"]) == (3, 2, 0b011)
+    pods = [e[3] for e in ctl.events if e[2] == "SuccessfulCreatePod"]
+    assert pods == ["sc-master-0", "sc-worker-0", "sc-worker-1"]     # survivors were never restarted
+    assert len(ctl.free_gpus) == 3
+
+
+def test_full_box_keeps_low_priority_job_queued_so_priority_wins(tok_lib, tmp_path, monkeypatch):
+    """Quota filter sees real GPU usage (quota.go:97-131): while job a holds every GPU, job b (other
+    tenant, same default quota) is NOT dequeued; a high-priority job c that arrives later in b's queue
+    is therefore admitted before b once a finishes."""
+    monkeypatch.setenv("RUN_S", "3")
+
+    def mk(name, queue, prio=None):
+        m = manifest(name, free_port(), queue=queue)
+        for tt in ("Master", "Worker"):
+            m["spec"]["torchTaskSpecs"][tt]["template"]["spec"]["containers"][0]["command"] = \
+                [sys.executable, os.path.join(HERE, "cpu_elastic_replica.py")]
+        if prio is not None:
+            m["spec"].setdefault("schedulingPolicy", {})["priority"] = prio
+        return m
+    ctl = Controller(num_gpus=2, rdzv_dir=str(tmp_path))
+    a = ctl.submit(mk("qa", "team-a"))
+    import time
+    t0 = time.time()
+    while time.time() - t0 < 20 and len(ctl.free_gpus) > 0:
+        ctl.tick()
+        time.sleep(0.05)
+    assert len(ctl.free_gpus) == 0
+    b = ctl.submit(mk("qb", "team-b", prio=1))
+    for _ in range(12):
+        ctl.tick()
+        time.sleep(0.05)
+    assert not ctl.jobs[b].dequeued                      # the box is full: b waits in its queue
+    c = ctl.submit(mk("qc", "team-b", prio=100))
+    res = ctl.run_until_done(timeout=90)
+    assert set(res.values()) == {"Succeeded"}, res
+    order = [e[1] for e in ctl.events if e[2] == "JobDequeued"]
+    assert order == [a, c, b]

@@ -523,3 +523,18 @@ def test_termination_policies_match_oracle_and_known_answers():
     bad = {"Master": [{"phase": "Running"}], "Worker": [{"phase": "Running", "restartCount": 2}]}
     r = j3.check_termination(bad, 0, "2026-01-01T00:00:02Z")
     assert r["terminate"] and r["pastBackoffLimit"] and "backoff limit" in r["message"]
+
+
+def test_dag_ready_with_zero_task_upstream_and_missing_phases(tok_lib):
+    """A Master with numTasks 0 and no phase entry for it must not crash the DAG gate (public C ABI
+    entry fed with external JSON); unknown / missing keys read as "no replicas yet"."""
+    m = {"metadata": {"name": "z"}, "spec": {"torchTaskSpecs": {
+        "Master": {"numTasks": 0, "template": {"spec": {"containers": [{"name": "torch", "image": "i"}]}}},
+        "Worker": {"numTasks": 2, "template": {"spec": {"containers": [{"name": "torch", "image": "i"}]}}}}}}
+    job = TorchJob(m)
+    assert job.dag_ready("Worker", {}) is True
+    assert job.dag_ready("Worker", {"Worker": ["Pending"]}) is True
+    assert job.dag_ready("Worker", {"Master": []}) is True
+    for phases in ({}, {"Master": "Running"}, {"master": [None]}, {"Master": [1, 2]}):
+        job.dag_ready("Master", phases)
+        job.dag_ready("Worker", phases)       # no crash on malformed values either

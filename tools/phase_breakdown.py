@@ -1,5 +1,7 @@
 """Per-phase timing of the exchange kernels (TOK_DEBUG_PHASES=1): for each algorithm and size, the
-median over CTAs and ranks of {stage, barrier A, reduce, barrier B, gather/copy-out}.  torchrun, one
+median over CTAs and ranks of {stage, barrier A, reduce, barrier B, gather/copy-out}.  The zero-copy
+kernels (rows *_inplace) have no stage / barrier A / copy-out: reduce+push, then the trailing barrier
+(barB); the arrival kernel in front of them is a separate launch and is not in `total`.  torchrun, one
 rank per GPU.  Not part of the product."""
 import ctypes as C
 import json
@@ -30,8 +32,10 @@ def main():
                             rendezvous_path="/tmp/tok8s-phase-%s-%d" % (os.environ["MASTER_PORT"], ctas))
         for mb in [float(x) for x in os.environ.get("SIZES_MB", "4,32,128").split(",")]:
             n = int(mb * (1 << 20)) // 2
-            bufs = [torch.full((n,), float(rank + 1), dtype=torch.bfloat16, device="cuda") for _ in range(4)]
-            for algo in (3, 4):
+            staged = [torch.full((n,), float(rank + 1), dtype=torch.bfloat16, device="cuda") for _ in range(4)]
+            pooled = [comm.symm_empty(n, torch.bfloat16).fill_(float(rank + 1)) for _ in range(4)]
+            for algo, zc in ((3, False), (4, False), (3, True), (4, True)):
+                bufs = pooled if zc else staged
                 if algo == 4 and not comm.caps().multicast:
                     continue
                 rows = []
@@ -57,7 +61,7 @@ def main():
                 t = torch.tensor([stat[k] for k in sorted(stat)], device="cuda", dtype=torch.float64)
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
                 row = dict(zip(sorted(stat), [round(float(x), 2) for x in t.tolist()]))
-                row.update(algo=_ffi.ALGO_NAMES[algo], mb=mb, world=world, ctas=ctas, n_ctas=int(a.shape[1]))
+                row.update(algo=comm.last_algo(), mb=mb, world=world, ctas=ctas, n_ctas=int(a.shape[1]))
                 out.append(row)
                 if rank == 0:
                     print(json.dumps(row), flush=True)

@@ -19,6 +19,7 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
+from bench import ClockSampler  # noqa: E402  (nvidia-smi clocks + throttle reasons during the run)
 from torch_on_k8s_b200 import _ffi  # noqa: E402
 from torch_on_k8s_b200.comm import Communicator  # noqa: E402
 
@@ -64,6 +65,9 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     stream = torch.cuda.Stream()
     results = []
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     cta_list = [int(x) for x in args.ctas.split(",") if x] or [0]
     for ctas in cta_list:
         if ctas:
@@ -104,13 +108,26 @@ def main():
                 # zero-copy: the same exchange on buckets that live in the symmetric pool
                 if args.zero_copy and world > 1 and nbytes >= (1 << 16):
                     zbufs = [comm.symm_empty(count, dt).fill_(float(rank + 1)) for _ in range(nbuf)]
-                    for algo, name in ((0, "zc_auto"), (3, "zc_two_shot")):
+                    zalgos = [(0, "zc_auto"), (3, "zc_two_shot")]
+                    if caps.multicast:
+                        zalgos.append((4, "zc_nvls"))
+                    for algo, name in zalgos:
                         def fnz(b, algo=algo):
                             comm.allreduce_bucket(b, b, scale=1.0, algo=algo, stream=stream)
                         ms = time_loop(fnz, zbufs, args.warmup, iters, stream)
                         comm.status()
                         row[name + "_us"] = ms * 1e3
                         row[name + "_busbw"] = nbytes / (ms * 1e-3) * 2 * (world - 1) / world / 1e9
+                        if algo == 0:
+                            row["zc_auto_kernel"] = comm.last_algo()
+                    # broadcast of the same bytes from rank 0 (parameter / state replication)
+                    def fnb(b):
+                        comm.broadcast(b, 0, stream=stream)
+                    ms = time_loop(fnb, zbufs, args.warmup, iters, stream)
+                    comm.status()
+                    row["bcast_pool_us"] = ms * 1e3
+                    row["bcast_pool_gbs"] = nbytes / (ms * 1e-3) / 1e9
+                    row["bcast_kernel"] = comm.last_algo()
                     zb = comm.symm_empty(count, dt).fill_(float(rank + 1))
                     with torch.cuda.stream(stream):
                         comm.allreduce_bucket(zb, zb, scale=1.0, stream=stream)
@@ -129,6 +146,11 @@ def main():
                     ms = time_loop(fn2, bufs, args.warmup, iters, stream)
                     row["nccl_us"] = ms * 1e3
                     row["nccl_busbw"] = nbytes / (ms * 1e-3) * 2 * (world - 1) / world / 1e9
+
+                    def fn3(b):
+                        dist.broadcast(b, 0)
+                    ms = time_loop(fn3, bufs, args.warmup, iters, stream)
+                    row["nccl_bcast_us"] = ms * 1e3
                 results.append(row)
                 if rank == 0:
                     print(json.dumps({k: (round(v, 2) if isinstance(v, float) else v)
@@ -140,7 +162,8 @@ def main():
     if rank == 0:
         os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
         with open("%s_n%d.json" % (args.out, world), "w") as f:
-            json.dump(dict(world=world, when=time.time(), rows=results), f, indent=1)
+            json.dump(dict(world=world, when=time.time(), clocks=sampler.stop(),
+                           gpu=torch.cuda.get_device_name(0), rows=results), f, indent=1)
     dist.destroy_process_group()
 
 

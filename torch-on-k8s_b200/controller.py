@@ -68,6 +68,8 @@ class ManagedJob:
     epoch: int = 0            # membership epoch of the job's peer group (bumped on every rescale)
     elastic: Optional[ElasticPolicy] = None
     elastic_due: float = 0.0
+    membership_dirty: bool = False     # the replica set changed since the last published epoch
+    published: Optional[dict] = None   # last membership document written
 
 
 class Controller:
@@ -128,10 +130,14 @@ class Controller:
     # ---- one controller pass ------------------------------------------------------------------------
     def tick(self, now: Optional[float] = None) -> None:
         now = time.monotonic() if now is None else now
-        used = self.num_gpus - len(self.free_gpus)
-        for tenant in {self._tenant(m) for m in self.jobs.values()}:
-            self.coord.set_used(tenant, 0)
-        self.coord.set_used("", used)
+        # ResourceQuota.used stand-in: GPUs held per tenant (for tenants with their own quota) and by
+        # the whole box (the default quota "" every other tenant is accounted against)
+        held: Dict[str, int] = {}
+        for m in self.jobs.values():
+            held[self._tenant(m)] = held.get(self._tenant(m), 0) + len(m.gpus)
+        for tenant, n in held.items():
+            self.coord.set_used(tenant, n)
+        self.coord.set_used("", self.num_gpus - len(self.free_gpus))
         out = self.coord.tick(now)
         if out.get("dequeued"):
             mj = self.jobs[out["dequeued"]]
@@ -205,9 +211,10 @@ class Controller:
             for idx in range(int(specs[tt].get("numTasks", 1))):
                 if idx not in have:
                     self._start_replica(mj, tt, idx)
-        if mj.epoch > 0 or changed:
-            if changed or sum(len(v) for v in mj.replicas.values()) != before:
-                self._publish_membership(mj)
+        if changed or sum(len(v) for v in mj.replicas.values()) != before:
+            mj.membership_dirty = True
+        if mj.epoch > 0 and mj.membership_dirty:
+            self._publish_membership(mj)     # deferred while a listed replica has no process yet
         reps = {tt: [dict(phase=r.phase, scheduled=r.gpu is not None or tt == "AIMaster",
                           exitCode=r.exit_code) for r in v.values()]
                 for tt, v in mj.replicas.items()}
@@ -256,31 +263,75 @@ class Controller:
         elif out["action"] in ("forget", "stop_managing"):
             mj.elastic_due = float("inf")
 
-    def _publish_membership(self, mj: ManagedJob) -> None:
+    # ---- user-driven rescale (row a7) ---------------------------------------------------------------
+    def scale(self, uid: str, task_type: str, num_tasks: int) -> int:
+        """A spec update of torchTaskSpecs[task_type].numTasks on a running job — what the reference
+        answers by restarting every stale pod with a new WORLD_SIZE (controllers/train/
+        elastic_scale.go:210-397).  Here the next reconcile creates / deletes the replicas and a new
+        membership epoch lets the survivors re-form in place.  Returns the new epoch."""
+        from ._ffi import TOK_MAX_WORLD
+        mj = self.jobs[uid]
+        others = sum(int(ts.get("numTasks", 1)) for tt, ts in mj.job.task_specs.items()
+                     if tt not in ("AIMaster", task_type))
+        if others + num_tasks > TOK_MAX_WORLD:
+            raise ValueError("world %d exceeds the box (%d replicas)" % (others + num_tasks, TOK_MAX_WORLD))
+        before = mj.job.num_tasks(task_type)
+        if before == num_tasks:
+            return mj.epoch
+        mj.job.scale(task_type, num_tasks)
+        mj.epoch += 1
+        mj.membership_dirty = True
+        self._event(uid, "Scale", "%s %d -> %d (epoch %d)" % (task_type, before, num_tasks, mj.epoch))
+        return mj.epoch
+
+    def _publish_membership(self, mj: ManagedJob) -> bool:
         """Membership epoch file next to the job's rendezvous socket: the in-place replacement of the
         reference's `distributed.io/world-size` annotation + kruise container restart
         (controllers/train/elastic_scale.go:303-397).  Replicas poll it (worker.Replica.poll_membership)
-        and call tok_comm_reform / join at the announced epoch."""
+        and call tok_comm_reform / join at the announced epoch.
+
+        Only a membership every member of which has a live process is announced: survivors that
+        re-formed towards a replica that is still Pending (no free GPU) would block in the rendezvous
+        until it times out — the reference's has_pending branch reverts such a scale-out instead, and
+        so does the next torchelastic pass here.  Returns True when a document was written."""
         import json
+        from ._ffi import TOK_MAX_WORLD
         members, mask = {}, 0
         for tt in TASK_ORDER:
             for idx in sorted(mj.replicas.get(tt, {})):
                 if tt == "AIMaster":
                     continue
+                r = mj.replicas[tt][idx]
+                if r.proc is None or r.proc.poll() is not None:
+                    return False            # Pending / exited: wait for the reconcile to settle
                 spec = mj.job.cluster_spec(tt.lower(), idx)
                 members[spec["name"]] = spec["rank"]
                 # a replica's rank is a function of (task type, index), so a survivor keeps its rank:
-                # bit i set <=> the replica that held rank i before this epoch is still a member
-                # (tok_comm_reform's member_mask)
-                if mj.replicas[tt][idx].epoch < mj.epoch:
+                # bit i set <=> the replica that held rank i in the membership the group currently
+                # runs with (the last PUBLISHED one, or the initial one) is still a member
+                # (tok_comm_reform's member_mask).  Replicas started since then are joiners, whatever
+                # epoch they were started at: they wait for this document and join at ITS epoch.
+                known = mj.published["ranks"] if mj.published is not None else None
+                if (known is not None and spec["name"] in known) or (known is None and r.epoch == 0):
                     mask |= 1 << spec["rank"]
+        world = mj.job.world_size
+        if len(members) != world or sorted(members.values()) != list(range(world)):
+            return False                    # replicas of the new spec are not all created yet
+        if world > TOK_MAX_WORLD:
+            self._event(mj.uid, "MembershipRejected", "world %d > %d" % (world, TOK_MAX_WORLD))
+            return False
+        mj.membership_dirty = False
+        if mj.published is not None and mj.published["ranks"] == members:
+            return False                    # e.g. a scale-out that was reverted before it happened
         port = mj.job.cluster_spec("master", 0)["env"][0]["value"]
         path = os.path.join(self.rdzv_dir, "tok8s-%s-%s.members" % (mj.job.name.replace("/", "-"), port))
-        doc = {"epoch": mj.epoch, "world": mj.job.world_size, "ranks": members, "survivor_mask": mask}
+        doc = {"epoch": mj.epoch, "world": world, "ranks": members, "survivor_mask": mask}
         with open(path + ".tmp", "w") as f:
             json.dump(doc, f)
         os.replace(path + ".tmp", path)
+        mj.published = doc
         self._event(mj.uid, "MembershipPublished", json.dumps(doc))
+        return True
 
     def _start_replica(self, mj: ManagedJob, tt: str, idx: int, restarts: int = 0) -> None:
         spec = mj.job.cluster_spec(tt.lower(), idx)

@@ -373,7 +373,7 @@ struct tok_comm {
   bool disable_nvls = false;
   unsigned long long barrier_timeout_ns = 600000ull * 1000000ull;
   double rdzv_timeout_s = 120;
-  int local_tma = 0;        // world 1, one dtype: 1 = cp.async.bulk variant, 0 = LDG.128 wave
+  int local_tma = 1;        // world 1, one dtype: 1 = cp.async.bulk variant, 0 = LDG.128 wave
 
   std::atomic<uint64_t> launches{0};    // exchange / broadcast / local kernels
   std::atomic<uint64_t> arrivals{0};    // arrive kernels
@@ -869,7 +869,10 @@ int create_impl(const char* job_id, int rank, int world, int max_world, int devi
   // NCCL's watchdog default is 600 s; replicas legitimately skew by tens of seconds (first-iteration
   // cuDNN autotune, evaluation or a checkpoint on rank 0)
   c->barrier_timeout_ns = env_size("TOK_BARRIER_TIMEOUT_MS", 600000) * 1000000ull;
-  c->local_tma = static_cast<int>(env_size("TOK_LOCAL_TMA", 0));
+  // measured (profiles/r02_local_bench_n1.json): the cp.async.bulk ring beats the LDG.128 wave at
+  // every size from 4 MB to 1 GiB (12.4 vs 14.5 us at the 28 MB DDP bucket, 0.97 vs 0.71-0.90 of the
+  // measured HBM peak at 1 GiB)
+  c->local_tma = static_cast<int>(env_size("TOK_LOCAL_TMA", 1));
   c->rdzv_timeout_s = static_cast<double>(env_size("TOK_RDZV_TIMEOUT_S", 120));
 
   int rc = TOK_OK;

@@ -160,18 +160,27 @@ Queue* wrr_next(tok_coord* c, std::string* name) {  // policy.go:104-221
 }
 
 // Quota filter (quota.go:97-131): Wait unless the tenant's free GPU slots cover the request.
+// The quota object a tenant is accounted against: its own ResourceQuota when one was set, else the
+// default ("" = the whole box).  Usage and 60 s assumptions live under the SAME key as the hard limit:
+// tenants that share the default quota see each other's GPUs (a job of tenant A holding every GPU
+// keeps tenant B's job queued, as ResourceQuota.used would in the reference, quota.go:97-131).
+const std::string& quota_key(const tok_coord* c, const Unit& u) {
+  static const std::string kDefault;
+  return c->hard.count(u.tenant) ? u.tenant : kDefault;
+}
+
 bool quota_ok(tok_coord* c, const Unit& u, double now, std::string* why) {
-  auto h = c->hard.find(u.tenant);
-  if (h == c->hard.end()) h = c->hard.find("");
+  const std::string& qk = quota_key(c, u);
+  auto h = c->hard.find(qk);
   if (h == c->hard.end()) return true;  // no quota object in this namespace: nothing to check
-  const int64_t used = c->used.count(u.tenant) ? c->used[u.tenant] : 0;
+  const int64_t used = c->used.count(qk) ? c->used[qk] : 0;
   if (used > h->second) {  // availableQuota: exceed (:134-143)
     *why = "queue " + u.tenant + " guaranteed quota has exceed";
     return false;
   }
   int64_t available = h->second - used;
   // accumulateAssumedQuota: drop stale assumptions first (:146-173, 256-277)
-  auto& as = c->assumed[u.tenant];
+  auto& as = c->assumed[qk];
   for (auto it = as.begin(); it != as.end();) {
     const bool expired = (now - it->second.ts) > kAssumeTimeout || c->settled.count(it->first);
     it = expired ? as.erase(it) : std::next(it);
@@ -373,7 +382,7 @@ int tok_coord_tick(tok_coord_t* c, double now, char** out) {
   }
   const Unit chosen = *candidates[sel].first;
   // PreDequeue: assume the quota (quota.go:176-181, 229-241)
-  c->assumed[chosen.tenant][chosen.uid] = Assumed{chosen.slots, now};
+  c->assumed[quota_key(c, chosen)][chosen.uid] = Assumed{chosen.slots, now};
   tok_coord_dequeue(c, chosen.uid.c_str());
   res["dequeued"] = Value::str(chosen.uid);
   res["key"] = Value::str(chosen.key);

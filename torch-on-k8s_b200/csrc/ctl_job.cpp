@@ -505,6 +505,7 @@ int tok_job_dag_ready(const tok_job_t* j, const char* task_type, const char* pha
       *ready = 0;
       return TOK_OK;
     }
+    if (!have || !have->is_array()) continue;  // upstream with numTasks 0 and no phase entry
     for (const Value& p : have->a)
       if (phase_code(p.as_string()) - phase_code(cond.second) < 0) {
         *ready = 0;

@@ -60,6 +60,25 @@ class TorchJob:
     def world_size(self) -> int:
         return sum(int(ts.get("numTasks", 1)) for tt, ts in self.task_specs.items() if tt != "AIMaster")
 
+    def scale(self, task_type: str, num_tasks: int) -> None:
+        """Edit spec.torchTaskSpecs[task_type].numTasks in place (`kubectl scale` / a spec update —
+        the trigger of the reference's annotation-driven rescale, controllers/train/elastic_scale.go:
+        210-397); status and every other field are preserved."""
+        d = self.to_dict()
+        specs = d["spec"]["torchTaskSpecs"]
+        if task_type not in specs:
+            raise KeyError("task type %s is not in spec.torchTaskSpecs" % task_type)
+        if num_tasks < 0:
+            raise ValueError("numTasks must be >= 0")
+        specs[task_type]["numTasks"] = int(num_tasks)
+        mm = d["spec"].get("minMembers")
+        if isinstance(mm, dict) and task_type in mm and int(mm[task_type]) > num_tasks:
+            mm[task_type] = int(num_tasks)     # MinMember may not exceed NumTasks (volcano.go:134-137)
+        h = C.c_void_p()
+        check(lib().tok_job_parse(json.dumps(d).encode(), C.byref(h)))
+        old, self._h = self._h, h
+        lib().tok_job_free(old)
+
     # SetClusterSpec
     def cluster_spec(self, task_type: str, index: int) -> dict:
         return call_json(lib().tok_job_cluster_spec, self._h, task_type.encode(), index)

@@ -137,8 +137,35 @@ def init_replica(job_id: Optional[str] = None, *, device: Optional[int] = None,
     # size changes while the process keeps running)
     if bootstrap_backend and not dist.is_initialized():
         dist.init_process_group(bootstrap_backend, rank=rank, world_size=world, device_id=dev)
-    comm = Communicator(job_id, rank, world, device, max_world=max_world,
-                        rendezvous_path=os.environ.get("TOK8S_RDZV") or
-                        default_rendezvous_path(job_id),
-                        epoch=int(os.environ.get("TOK8S_EPOCH", "0")))
+    rdzv = os.environ.get("TOK8S_RDZV") or default_rendezvous_path(job_id)
+    epoch = int(os.environ.get("TOK8S_EPOCH", "0"))
+    if epoch > 0:
+        # started into a running job (elastic scale-out): the controller announces the membership
+        # this replica belongs to once every member has a process; join at THAT epoch with the rank /
+        # world it states (a scale-out that was reverted first never lists this replica)
+        rank, world, epoch = wait_for_membership(rdzv, os.environ.get("TOK8S_REPLICA", ""), epoch)
+    comm = Communicator(job_id, rank, world, device, max_world=max_world, rendezvous_path=rdzv,
+                        epoch=epoch)
     return Replica(rank=rank, world=world, device=dev, comm=comm, job_id=job_id)
+
+
+def wait_for_membership(rdzv_path: str, replica_name: str, min_epoch: int,
+                        timeout_s: Optional[float] = None):
+    """(rank, world, epoch) of the first published membership with epoch >= min_epoch that lists
+    `replica_name` (controller.Controller._publish_membership writes <rendezvous>.members)."""
+    import json
+    import time
+    deadline = time.time() + (timeout_s if timeout_s is not None else
+                              float(os.environ.get("TOK_RDZV_TIMEOUT_S", "120")))
+    while True:
+        try:
+            with open(rdzv_path + ".members") as f:
+                doc = json.load(f)
+            if int(doc.get("epoch", 0)) >= min_epoch and replica_name in doc.get("ranks", {}):
+                return int(doc["ranks"][replica_name]), int(doc["world"]), int(doc["epoch"])
+        except (OSError, ValueError):
+            pass
+        if time.time() > deadline:
+            raise TimeoutError("no membership listing %s at epoch >= %d was published under %s" %
+                               (replica_name, min_epoch, rdzv_path + ".members"))
+        time.sleep(0.02)
