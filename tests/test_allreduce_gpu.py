@@ -222,7 +222,8 @@ def test_zero_copy_symmetric_pool(tok_lib, n_gpus, world):
                           scale=1.0 / 3.0, post=True, symm=True, pattern="wide",
                           expect_kernel="two_shot_inplace"))
         seed += 1   # AUTO + PRE with a factor that is not a power of two must stay on the exact kernel
-        cases.append(dict(count=(9 << 20) // 2, **{"in": dt, "wire": dt, "out": dt}, algo=0, seed=seed,
+        # (> 16 MiB: below that AUTO takes the one-shot kernel at N=2, pool bucket or not)
+        cases.append(dict(count=9 << 20, **{"in": dt, "wire": dt, "out": dt}, algo=0, seed=seed,
                           scale=1.0 / 3.0, symm=True, split=True, expect_kernel="two_shot_inplace"))
     # not a whole number of 16-byte packs -> staged path, still correct
     cases.append(dict(count=65536 + 3, **{"in": "bf16", "wire": "bf16", "out": "bf16"}, algo=3,
@@ -331,7 +332,7 @@ def test_nvls_tolerance(tok_lib, n_gpus):
                           pattern="ints", expect_kernel=auto_kernel if pow2 else None))
         exact_ids.add(670 + i)
     # f16 PRE buckets never take the in-switch sum (it could overflow before the 1/N)
-    cases.append(dict(count=1 << 20, **{"in": "f16", "wire": "f16", "out": "f16"}, algo=0, seed=690,
+    cases.append(dict(count=17 << 20, **{"in": "f16", "wire": "f16", "out": "f16"}, algo=0, seed=690,
                       scale=1.0 / world, symm=True, expect_kernel="two_shot_inplace"))
     res = harness.launch(world, cases, devices=list(range(world)), mode="proc", timeout=600)
     for rank, rs in res.items():
