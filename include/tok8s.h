@@ -196,6 +196,11 @@ int tok_comm_stats(tok_comm_t* comm, tok_stats_t* stats);
  * end}; this copies the last launch's stamps to the host (synchronises).                       */
 int tok_comm_debug_read(tok_comm_t* comm, uint64_t* out, size_t words);
 
+/* Profiling aid: `count` cross-replica barriers back to back in one launch of `ctas` CTAs and nothing
+ * else (variant 0 = the production barrier; 1 = P2P flags; 2 / 3 = signalling only, no ordering;
+ * 4 = production barrier behind a 64 KiB tail of posted peer stores) — tools/barrier_bench.py.    */
+int tok_comm_debug_barrier(tok_comm_t* comm, int variant, int ctas, size_t count, void* cuda_stream);
+
 /* ---- control plane (TorchJob surface) ------------------------------------------------------
  * JSON in, JSON out.  `tok_job_t` is a parsed + defaulted TorchJob (apis/train/v1alpha1).        */
 

@@ -70,12 +70,21 @@ class ManagedJob:
     elastic_due: float = 0.0
     membership_dirty: bool = False     # the replica set changed since the last published epoch
     published: Optional[dict] = None   # last membership document written
+    draining: List[tuple] = field(default_factory=list)   # (replica, name, deadline) leaving by itself
 
 
 class Controller:
     def __init__(self, num_gpus: int = 8, *, policy: str = "wrr", log_dir: Optional[str] = None,
                  rdzv_dir: str = "/tmp", state_dir: Optional[str] = None,
-                 elastic_period: float = LOOP_PERIOD_S):
+                 elastic_period: float = LOOP_PERIOD_S, drain_grace_s: float = 0.0,
+                 gpu_map: Optional[List[int]] = None):
+        """num_gpus GPU slots (one replica each).  gpu_map[slot] = physical CUDA ordinal (default:
+        identity; a test box with one GPU maps every slot to 0).  drain_grace_s > 0: a replica that
+        is scaled in is first dropped from the published membership and given that long to leave at
+        a step boundary of its own accord (in-place scale-in: its peers must not find it dead in the
+        middle of a gradient exchange); 0 = delete immediately (reconcileOnePod, pod.go:648-651)."""
+        self.drain_grace_s = drain_grace_s
+        self.gpu_map = gpu_map
         self.free_gpus = list(range(num_gpus))
         self.num_gpus = num_gpus
         self.coord = Coordinator(policy=policy)
@@ -187,19 +196,28 @@ class Controller:
         # replicas whose index fell out of [0, numTasks) are scaled down (reconcileOnePod,
         # controllers/common/pod.go:648-651)
         changed = False
+        for r, name, deadline in list(mj.draining):
+            gone = r.proc is None or r.proc.poll() is not None
+            if not gone and time.monotonic() > deadline:
+                self._kill(r)
+                gone = True
+            if gone:
+                mj.draining.remove((r, name, deadline))
+                self._release(mj, r)
+                self._event(mj.uid, "SuccessfulDeletePod", name)
         for tt, have in mj.replicas.items():
             n = int(specs.get(tt, {}).get("numTasks", 1)) if tt in specs else 0
             for idx in [i for i in have if i >= n]:
                 r = have.pop(idx)
-                if r.proc and r.proc.poll() is None:
-                    try:
-                        os.killpg(r.proc.pid, signal.SIGTERM)
-                        r.proc.wait(timeout=10)
-                    except (ProcessLookupError, subprocess.TimeoutExpired):
-                        pass
-                self._release(mj, r)
-                self._event(mj.uid, "SuccessfulDeletePod", "%s-%s-%d" % (job.name, tt.lower(), idx))
+                name = "%s-%s-%d" % (job.name, tt.lower(), idx)
                 changed = True
+                if r.proc and r.proc.poll() is None and self.drain_grace_s > 0:
+                    mj.draining.append((r, name, time.monotonic() + self.drain_grace_s))
+                    self._event(mj.uid, "DrainingPod", name)
+                    continue
+                self._kill(r)
+                self._release(mj, r)
+                self._event(mj.uid, "SuccessfulDeletePod", name)
         before = sum(len(v) for v in mj.replicas.values())
         for tt in TASK_ORDER + [k for k in specs if k not in TASK_ORDER]:
             if tt not in specs:
@@ -351,7 +369,8 @@ class Controller:
                    TOK8S_RDZV=os.path.join(self.rdzv_dir, "tok8s-%s-%s" %
                                            (mj.job.name.replace("/", "-"), env["MASTER_PORT"])))
         if gpu is not None:
-            env.update(TOK8S_GPU=str(gpu), LOCAL_RANK=str(gpu))
+            phys = self.gpu_map[gpu] if self.gpu_map else gpu
+            env.update(TOK8S_GPU=str(phys), LOCAL_RANK=str(phys), TOK8S_SLOT=str(gpu))
         cmd = mj.command or self._container_command(mj, tt)
         cmd = list(cmd) + spec["args"] if spec["args"] and mj.command is None else list(cmd)
         log = None
@@ -412,6 +431,15 @@ class Controller:
                         self._start_replica(mj, tt, idx, restarts=n)   # kubelet-style in-place restart
         return restarting
 
+    @staticmethod
+    def _kill(r: ReplicaProc) -> None:
+        if r.proc and r.proc.poll() is None:
+            try:
+                os.killpg(r.proc.pid, signal.SIGTERM)
+                r.proc.wait(timeout=10)
+            except (ProcessLookupError, subprocess.TimeoutExpired):
+                pass
+
     def _release(self, mj: ManagedJob, r: ReplicaProc) -> None:
         if r.gpu is not None and r.gpu in mj.gpus:
             mj.gpus.remove(r.gpu)
@@ -422,6 +450,10 @@ class Controller:
     def _finish(self, mj: ManagedJob, delete_pods: str = "None") -> None:
         # deletePodsAndServices (job.go:433-460): cleanPodPolicy None keeps everything, Running / All
         # stop what is still running (finished processes have nothing left to delete on one box)
+        for r, name, _ in mj.draining:
+            self._kill(r)
+            self._release(mj, r)
+        mj.draining = []
         for reps in mj.replicas.values():
             for r in reps.values():
                 if r.proc and r.proc.poll() is None and delete_pods in ("Running", "All"):

@@ -35,6 +35,8 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
+#include <string.h>
+
 #include <type_traits>
 
 #include "tok_internal.h"
@@ -652,9 +654,10 @@ struct AR {
         if (p < a.world) {
           float v[P];
           CW::to_f32(r[p], v);
-          if (pre != 1.f) {  // wire_p = cast_wire(f32(in_p) * pre)
+          if (pre != 1.f) {  // wire_p = cast_wire(f32(in_p) * pre); __fmul_rn: a separately rounded
+                             // product, never contracted with the sum below into an FMA
 #pragma unroll
-            for (int k = 0; k < P; ++k) v[k] *= pre;
+            for (int k = 0; k < P; ++k) v[k] = __fmul_rn(v[k], pre);
             const RW w = CW::from_f32(v);
             CW::to_f32(w, v);
           }
@@ -986,6 +989,9 @@ __global__ void __launch_bounds__(kThreads, 1) nvls_kernel(const __grid_constant
 // replica announces the heap offset of its bucket (buf_off != 0) and compares.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(32) arrive_kernel(const __grid_constant__ KArgs a) {
+  // programmatic dependent launch: an exchange kernel launched behind this one with the PDL attribute
+  // may become resident now; it parks in griddepcontrol.wait until this grid has completed
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int lane = threadIdx.x;
   const uint32_t target = a.ctr[kCtrArrive] + 1;
   const bool polls = lane < a.world;
@@ -1026,6 +1032,7 @@ __global__ void __launch_bounds__(kThreads, 1) nvls_inplace_kernel(const __grid_
   using A = AR<WIRE, WIRE, WIRE>;
   __shared__ uint32_t s_words[3];
   __shared__ int s_fail;
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // no-op unless launched with the PDL attribute
   CtaState st = cta_begin(a, s_words, &s_fail);
   const size_t lo = static_cast<size_t>(blockIdx.x) * a.packs_per_cta;
   const size_t hi = min_sz(lo + a.packs_per_cta, a.total_packs);
@@ -1053,6 +1060,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   using A = AR<WIRE, WIRE, WIRE>;
   __shared__ uint32_t s_words[3];
   __shared__ int s_fail;
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // no-op unless launched with the PDL attribute
   CtaState st = cta_begin(a, s_words, &s_fail);
   const float pre = (a.flags & TOK_FLAG_SCALE_POST) ? 1.f : a.scale;
   const float post = (a.flags & TOK_FLAG_SCALE_POST) ? a.scale : 1.f;
@@ -1169,6 +1177,77 @@ __global__ void __launch_bounds__(kThreads, 1) bcast_kernel(const __grid_constan
 }
 
 // ------------------------------------------------------------------------------------------------
+// Profiling aid (tools/barrier_bench.py): `count` cross-replica barriers back to back, nothing else —
+// what one barrier costs, and which part of it.  Variants:
+//   0 production barrier (multimem.red.release when a multicast mapping exists, else P2P flags)
+//   1 production P2P-flag barrier even when a multicast mapping exists
+//   2 signalling only: relaxed multimem.red + relaxed poll, no release, no acquire fence
+//   3 signalling only over P2P flags: relaxed stores + relaxed polls
+//   4 as 0, with 64 KiB of posted P2P / multicast stores in front of every barrier (a data tail)
+// Uses the flag words of CTA slots [128, 128 + grid) so that it never disturbs the exchange state.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 1) barrier_bench_kernel(const __grid_constant__ KArgs a) {
+  __shared__ int s_fail;
+  const int variant = static_cast<int>(a.flags);
+  const int slot = 128 + blockIdx.x;
+  if (threadIdx.x == 0) s_fail = 0;
+  uint32_t bar = a.ctr[slot];
+  __syncthreads();
+  for (size_t it = 0; it < a.count; ++it) {
+    bar += 1;
+    if (variant == 4) {
+      uint4* dst = reinterpret_cast<uint4*>(a.peer[(a.rank + 1) % a.world] + a.stage_off[0]) +
+                   static_cast<size_t>(blockIdx.x) * 4096;
+      const uint4 v = make_uint4(bar, bar, bar, bar);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) dst[threadIdx.x + k * kThreads] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      const int lane = threadIdx.x;
+      const bool use_mc = a.mc != nullptr && (variant == 0 || variant == 2 || variant == 4);
+      const bool ordered = variant == 0 || variant == 1 || variant == 4;
+      const uint32_t* word;
+      uint32_t want;
+      bool polls;
+      if (use_mc) {
+        uint32_t* mcw = reinterpret_cast<uint32_t*>(a.mc + kMcntOff) + slot;
+        if (lane == 0) {
+          if (ordered)
+            multimem_red_release_add(mcw, 1u);
+          else
+            asm volatile("multimem.red.relaxed.sys.global.add.u32 [%0], %1;" ::"l"(mcw), "r"(1u)
+                         : "memory");
+        }
+        word = reinterpret_cast<const uint32_t*>(a.peer[a.rank] + kMcntOff) + slot;
+        want = bar * static_cast<uint32_t>(a.world);
+        polls = lane == 0;
+      } else {
+        polls = lane < a.world;
+        if (polls) {
+          uint32_t* dst = reinterpret_cast<uint32_t*>(a.peer[lane]) + (slot * kMaxWorld + a.rank);
+          if (ordered)
+            st_release_sys(dst, bar);
+          else
+            asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(dst), "r"(bar) : "memory");
+        }
+        word = reinterpret_cast<const uint32_t*>(a.peer[a.rank]) + (slot * kMaxWorld + (polls ? lane : 0));
+        want = bar;
+      }
+      const int code = warp_spin(a, word, want, polls);
+      if (code != 0 && lane == 0) {
+        a.hostctl[kCtlStatus] = code;
+        s_fail = 1;
+      }
+      if (ordered) fence_sys();
+    }
+    __syncthreads();
+    if (s_fail) break;
+  }
+  if (threadIdx.x == 0) a.ctr[slot] = bar;
+}
+
+// ------------------------------------------------------------------------------------------------
 // dispatch
 // ------------------------------------------------------------------------------------------------
 template <class IN, class WIRE, class OUT>
@@ -1201,10 +1280,27 @@ int launch_typed(int algo, int ctas, const KArgs& a, cudaStream_t s) {
     case kAlgoTwoShotInplace:
     case kAlgoNvlsInplace:
       if constexpr (std::is_same<IN, WIRE>::value && std::is_same<WIRE, OUT>::value) {
+        // a.root doubles as the PDL switch for these kernels (it is only meaningful for broadcast):
+        // launched with programmatic stream serialization the CTAs become resident while the arrival
+        // kernel in front is still waiting and start the moment it completes
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(ctas);
+        cfg.blockDim = dim3(kThreads);
+        cfg.stream = s;
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr.val.programmaticStreamSerializationAllowed = 1;
+        if (a.root == 1) {
+          cfg.attrs = &attr;
+          cfg.numAttrs = 1;
+        }
+        cudaError_t le;
         if (algo == kAlgoNvlsInplace)
-          nvls_inplace_kernel<WIRE><<<ctas, kThreads, 0, s>>>(a);
+          le = cudaLaunchKernelEx(&cfg, nvls_inplace_kernel<WIRE>, a);
         else
-          two_shot_inplace_kernel<WIRE><<<ctas, kThreads, 0, s>>>(a);
+          le = cudaLaunchKernelEx(&cfg, two_shot_inplace_kernel<WIRE>, a);
+        if (le != cudaSuccess) return static_cast<int>(le);
         break;
       }
       return static_cast<int>(cudaErrorInvalidValue);
@@ -1246,6 +1342,11 @@ size_t local_tma_smem_bytes() { return kTmaStages * kTmaTileBytes + 64; }
 
 int launch_arrive(const KArgs& args, void* stream) {
   arrive_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(args);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int launch_barrier_bench(int ctas, const KArgs& args, void* stream) {
+  barrier_bench_kernel<<<ctas, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(args);
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -374,6 +374,7 @@ struct tok_comm {
   unsigned long long barrier_timeout_ns = 600000ull * 1000000ull;
   double rdzv_timeout_s = 120;
   int local_tma = 1;        // world 1, one dtype: 1 = cp.async.bulk variant, 0 = LDG.128 wave
+  int pdl = 0;              // zero-copy exchange kernels use programmatic dependent launch
 
   std::atomic<uint64_t> launches{0};    // exchange / broadcast / local kernels
   std::atomic<uint64_t> arrivals{0};    // arrive kernels
@@ -873,6 +874,7 @@ int create_impl(const char* job_id, int rank, int world, int max_world, int devi
   // every size from 4 MB to 1 GiB (12.4 vs 14.5 us at the 28 MB DDP bucket, 0.97 vs 0.71-0.90 of the
   // measured HBM peak at 1 GiB)
   c->local_tma = static_cast<int>(env_size("TOK_LOCAL_TMA", 1));
+  c->pdl = static_cast<int>(env_size("TOK_PDL", 0));
   c->rdzv_timeout_s = static_cast<double>(env_size("TOK_RDZV_TIMEOUT_S", 120));
 
   int rc = TOK_OK;
@@ -1261,9 +1263,13 @@ int plan_bucket(const tok_comm* c, const void* in, const void* out, size_t count
   }
   // Zero-copy: the bucket lives in the symmetric pool (same offset on every replica), is exchanged
   // in place, in its own dtype, in whole 16-byte packs -> peers read / multicast it directly.
-  bool inplace = c->zero_copy && !(flags & TOK_FLAG_NO_ZERO_COPY) && in == out && same_dt &&
-                 in_pool(c, in, count * isz) && (count * wsz) % 16 == 0 &&
-                 (algo == TOK_ALGO_TWO_SHOT || algo == TOK_ALGO_NVLS);
+  const bool pool_ok = c->zero_copy && !(flags & TOK_FLAG_NO_ZERO_COPY) && in == out && same_dt &&
+                       in_pool(c, in, count * isz) && (count * wsz) % 16 == 0;
+  // a pool bucket leaves the one-shot range earlier: its exchange needs no staging pass (measured at
+  // N=2, profiles/r02_sweep_n2.json: in place 30.9 vs one-shot 30.0 us at 8 MiB, 43.6 vs 47.0 at 16)
+  if (!forced && algo == TOK_ALGO_ONE_SHOT && pool_ok && c->world == 2 && count * wsz >= (8u << 20))
+    algo = TOK_ALGO_TWO_SHOT;
+  bool inplace = pool_ok && (algo == TOK_ALGO_TWO_SHOT || algo == TOK_ALGO_NVLS);
   if (inplace) {
     // The switch can only scale the SUM.  That equals the specified PRE semantics (scale every
     // contribution, then sum) when the caller asked for POST or the factor is a power of two; a
@@ -1371,6 +1377,7 @@ int tok_allreduce_bucket(tok_comm_t* c, const void* in, void* out, size_t count,
   a.buf_off = pl.buf_off;
   a.scale = scale;
   a.flags = flags & TOK_FLAG_SCALE_POST;
+  a.root = (inplace && c->pdl) ? 1 : 0;  // PDL switch of the zero-copy kernels
 
   for (size_t off = 0; off < count; off += launch_cap) {
     const size_t n = std::min(launch_cap, count - off);
@@ -1425,6 +1432,25 @@ int tok_allreduce_bucket(tok_comm_t* c, const void* in, void* out, size_t count,
   return TOK_OK;
 }
 
+int tok_comm_debug_barrier(tok_comm_t* c, int variant, int ctas, size_t count, void* cuda_stream) {
+  if (!c) return fail(TOK_ERR_INVALID, "comm is null");
+  if (variant < 0 || variant > 4 || ctas < 1 || ctas > 64)
+    return fail(TOK_ERR_INVALID, "variant 0..4, ctas 1..64");
+  if (c->world < 2) return fail(TOK_ERR_STATE, "a barrier needs world >= 2");
+  int st = tok_comm_status(c);
+  if (st != TOK_OK) return st;
+  DeviceGuard guard(c->device);
+  KArgs a;
+  fill_common(c, &a);
+  a.count = count;
+  a.flags = static_cast<uint32_t>(variant);
+  int e = launch_barrier_bench(ctas, a, cuda_stream);
+  if (e != 0)
+    return fail(TOK_ERR_CUDA, "barrier bench launch failed: %s",
+                cudaGetErrorString(static_cast<cudaError_t>(e)));
+  return TOK_OK;
+}
+
 int tok_broadcast(tok_comm_t* c, void* buf, size_t bytes, int root, void* cuda_stream) {
   if (!c) return fail(TOK_ERR_INVALID, "comm is null");
   if (root < 0 || root >= c->world)
@@ -1442,7 +1468,7 @@ int tok_broadcast(tok_comm_t* c, void* buf, size_t bytes, int root, void* cuda_s
   a.root = root;
   auto grid = [&](size_t nbytes, KArgs* k) {
     const size_t packs = std::max<size_t>(nbytes / 16, 1);
-    const size_t g = std::min<size_t>(std::max<size_t>((nbytes + c->cta_bytes - 1) / c->cta_bytes, 1), 64);
+    const size_t g = std::min<size_t>(std::max<size_t>((nbytes + c->cta_bytes - 1) / c->cta_bytes, 1), 128);
     k->packs_per_cta = (packs + g - 1) / g;
     return static_cast<int>((packs + k->packs_per_cta - 1) / k->packs_per_cta);
   };
@@ -1454,7 +1480,9 @@ int tok_broadcast(tok_comm_t* c, void* buf, size_t bytes, int root, void* cuda_s
     a.in = buf;
     a.out = buf;
     a.count = bytes;
-    const int mode = c->mc_va ? kBcastMcPush : kBcastPull;
+    // one multimem.st stream feeds N-1 receivers; with a single receiver it saves nothing and a
+    // pull (the receiver's own LDG.128 over NVLink) is the faster copy
+    const int mode = (c->mc_va && c->world >= 3) ? kBcastMcPush : kBcastPull;
     const int ctas = grid(bytes, &a);
     int e = launch_broadcast(mode, ctas, a, cuda_stream);
     if (e != 0)

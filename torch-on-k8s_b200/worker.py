@@ -81,10 +81,12 @@ class Replica:
             broadcast_coalesced(self.comm, ts, root)
 
     def poll_membership(self):
-        """Elastic add/drop without a restart: read the membership epoch file the controller writes
-        next to the rendezvous socket (controller.Controller._publish_membership) and, when the epoch
-        moved, re-form the peer group in place (tok_comm_reform).  Returns the new (rank, world), or
-        None when nothing changed or this replica is no longer a member."""
+        """Elastic add/drop without a restart, single-replica view: read the membership epoch file
+        the controller writes next to the rendezvous socket (controller.Controller._publish_membership)
+        and, when the epoch moved, re-form the peer group in place (tok_comm_reform).  Returns the new
+        (rank, world), or None when nothing changed or this replica is no longer a member.
+        Replicas that are in the middle of a training loop must agree on the STEP at which they
+        re-form — use poll_membership_collective()."""
         import json
         try:
             with open(self.comm.rendezvous_path + ".members") as f:
@@ -98,6 +100,52 @@ class Replica:
         self.comm.reform(new_world, new_rank, mask, epoch)
         self.rank, self.world = new_rank, new_world
         return self.rank, self.world
+
+    def poll_membership_collective(self):
+        """The same decision taken by the whole group at one step boundary: rank 0's view of the
+        published epoch is replicated with tok_broadcast (a 16-byte bucket), so every replica leaves
+        the old group at the same step — a replica that re-formed one step earlier than its peers
+        would wait in the rendezvous while they wait for it in the gradient exchange.
+        Returns ("reformed", rank, world), ("dropped",) when the new membership no longer lists this
+        replica (it must stop using the communicator and exit), or None."""
+        import json
+        import time
+        cur = self.comm.caps().epoch
+        seen = 0
+        try:
+            with open(self.comm.rendezvous_path + ".members") as f:
+                seen = int(json.load(f).get("epoch", 0))
+        except (OSError, ValueError):
+            seen = 0
+        if self.world > 1:
+            if getattr(self, "_epoch_cell", None) is None:
+                self._epoch_cell = torch.zeros(2, dtype=torch.int64, device=self.device)
+            self._epoch_cell[0] = seen
+            self.comm.broadcast(self._epoch_cell, 0)
+            seen = int(self._epoch_cell[0].item())      # rank 0's view, the same on every replica
+        if seen <= cur:
+            return None
+        me = os.environ.get("TOK8S_REPLICA", "")
+        deadline = time.time() + 30.0
+        while True:                                      # rank 0 saw it: the file is there
+            try:
+                with open(self.comm.rendezvous_path + ".members") as f:
+                    doc = json.load(f)
+                if int(doc.get("epoch", 0)) >= seen:
+                    break
+            except (OSError, ValueError):
+                pass
+            if time.time() > deadline:
+                raise TimeoutError("membership epoch %d announced by rank 0 is not readable" % seen)
+            time.sleep(0.005)
+        step = membership_update(doc, me, cur)
+        if step is None:
+            return ("dropped",)
+        new_world, new_rank, mask, epoch = step
+        torch.cuda.current_stream(self.device).synchronize()
+        self.comm.reform(new_world, new_rank, mask, epoch)
+        self.rank, self.world = new_rank, new_world
+        return ("reformed", new_rank, new_world)
 
     def close(self):
         self.comm.close()
