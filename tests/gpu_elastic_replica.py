@@ -16,10 +16,12 @@ from workloads.mlp import batch, mlp  # noqa: E402
 
 steps = int(os.environ.get("STEPS", "400"))
 pace = float(os.environ.get("PACE_S", "0.02"))
-rep = init_replica(bootstrap_backend=None, max_world=int(os.environ.get("MAX_WORLD", "4")))
+gpu = int(os.environ["TOK8S_GPU"])
+torch.cuda.set_device(gpu)
+model = mlp(0 if int(os.environ.get("TOK8S_EPOCH", "0")) == 0 else 99).cuda(gpu)   # joiners start "wrong"
+rep = init_replica(bootstrap_backend=None, device=gpu, max_world=int(os.environ.get("MAX_WORLD", "4")))
 name = os.environ["TOK8S_REPLICA"]
 dev = rep.device
-model = mlp(0 if rep.comm.caps().epoch == 0 else 99).to(dev)      # joiners start "wrong"
 edp = ElasticDataParallel(model, rep.comm)
 opt = torch.optim.SGD(model.parameters(), lr=0.05, momentum=0.9)
 x, y = batch(rep.rank, 64)

@@ -66,14 +66,14 @@ def progress(log_dir, replica):
 def test_controller_rescales_gpu_job_in_place(tok_lib, n_gpus, tmp_path, monkeypatch):
     from torch_on_k8s_b200.controller import Controller
     monkeypatch.setenv("OUT_DIR", str(tmp_path))
-    monkeypatch.setenv("STEPS", "260")
+    monkeypatch.setenv("STEPS", "2500")
     monkeypatch.setenv("TOK_RDZV_TIMEOUT_S", "90")
     for k, v in dict(TOK_MAX_CTAS="16", TOK_STAGING_MB="16", TOK_SYMM_POOL_MB="32",
                      TOK_BARRIER_TIMEOUT_MS="120000").items():
         monkeypatch.setenv(k, v)
     logs = str(tmp_path / "logs")
     ctl = Controller(num_gpus=4, log_dir=logs, rdzv_dir=str(tmp_path), drain_grace_s=60,
-                     gpu_map=[i % max(n_gpus, 1) for i in range(4)])
+                     gpu_map=[i % max(n_gpus, 1) for i in range(4)], wait_ready=True)
     uid = ctl.submit(manifest("el", workers=1))
     assert wait_for(lambda: progress(logs, "el-master-0") >= 20, ctl, 180), ctl.events[-6:]
     assert ctl.scale(uid, "Worker", 3) == 1                     # world 2 -> 4
@@ -83,10 +83,14 @@ def test_controller_rescales_gpu_job_in_place(tok_lib, n_gpus, tmp_path, monkeyp
     assert ctl.scale(uid, "Worker", 1) == 2                     # world 4 -> 2
     assert wait_for(lambda: sum(e[2] == "SuccessfulDeletePod" for e in ctl.events) == 2, ctl, 120), \
         ctl.events[-8:]
-    res = ctl.run_until_done(timeout=240)
+    res = ctl.run_until_done(timeout=400)
     assert res[uid] == "Succeeded", ctl.events[-8:]
     pods = [e[3] for e in ctl.events if e[2] == "SuccessfulCreatePod"]
     assert pods == ["el-master-0", "el-worker-0", "el-worker-1", "el-worker-2"]   # nobody restarted
+    # the scale-out was announced only once both joiners were up: the survivors trained on meanwhile
+    t_pub = [e[0] for e in ctl.events if e[2] == "MembershipPublished"][0]
+    t_new = [e[0] for e in ctl.events if e[2] == "SuccessfulCreatePod"][-1]
+    assert t_pub - t_new > 1.0
     drained = [e[3] for e in ctl.events if e[2] == "DrainingPod"]
     assert sorted(drained) == ["el-worker-1", "el-worker-2"]
     assert len(ctl.free_gpus) == 4

@@ -77,7 +77,7 @@ class Controller:
     def __init__(self, num_gpus: int = 8, *, policy: str = "wrr", log_dir: Optional[str] = None,
                  rdzv_dir: str = "/tmp", state_dir: Optional[str] = None,
                  elastic_period: float = LOOP_PERIOD_S, drain_grace_s: float = 0.0,
-                 gpu_map: Optional[List[int]] = None):
+                 gpu_map: Optional[List[int]] = None, wait_ready: bool = False):
         """num_gpus GPU slots (one replica each).  gpu_map[slot] = physical CUDA ordinal (default:
         identity; a test box with one GPU maps every slot to 0).  drain_grace_s > 0: a replica that
         is scaled in is first dropped from the published membership and given that long to leave at
@@ -85,6 +85,10 @@ class Controller:
         middle of a gradient exchange); 0 = delete immediately (reconcileOnePod, pod.go:648-651)."""
         self.drain_grace_s = drain_grace_s
         self.gpu_map = gpu_map
+        # wait_ready: announce a scale-out only when every joiner has written its readiness marker
+        # (worker.init_replica does, once CUDA is up and the script's model is built): the survivors
+        # then pause for the re-form and the state hand-over only, not for the joiners' start-up
+        self.wait_ready = wait_ready
         self.free_gpus = list(range(num_gpus))
         self.num_gpus = num_gpus
         self.coord = Coordinator(policy=policy)
@@ -323,14 +327,19 @@ class Controller:
                 if r.proc is None or r.proc.poll() is not None:
                     return False            # Pending / exited: wait for the reconcile to settle
                 spec = mj.job.cluster_spec(tt.lower(), idx)
+                known = mj.published["ranks"] if mj.published is not None else None
+                joiner = (known is not None and spec["name"] not in known) or \
+                    (known is None and r.epoch > 0)
+                if self.wait_ready and joiner and not os.path.exists(
+                        "%s.ready.%s" % (self._rdzv_path(mj), spec["name"])):
+                    return False            # still starting up: the survivors keep training
                 members[spec["name"]] = spec["rank"]
                 # a replica's rank is a function of (task type, index), so a survivor keeps its rank:
                 # bit i set <=> the replica that held rank i in the membership the group currently
                 # runs with (the last PUBLISHED one, or the initial one) is still a member
                 # (tok_comm_reform's member_mask).  Replicas started since then are joiners, whatever
                 # epoch they were started at: they wait for this document and join at ITS epoch.
-                known = mj.published["ranks"] if mj.published is not None else None
-                if (known is not None and spec["name"] in known) or (known is None and r.epoch == 0):
+                if not joiner:
                     mask |= 1 << spec["rank"]
         world = mj.job.world_size
         if len(members) != world or sorted(members.values()) != list(range(world)):
@@ -341,8 +350,7 @@ class Controller:
         mj.membership_dirty = False
         if mj.published is not None and mj.published["ranks"] == members:
             return False                    # e.g. a scale-out that was reverted before it happened
-        port = mj.job.cluster_spec("master", 0)["env"][0]["value"]
-        path = os.path.join(self.rdzv_dir, "tok8s-%s-%s.members" % (mj.job.name.replace("/", "-"), port))
+        path = self._rdzv_path(mj) + ".members"
         doc = {"epoch": mj.epoch, "world": world, "ranks": members, "survivor_mask": mask}
         with open(path + ".tmp", "w") as f:
             json.dump(doc, f)
@@ -350,6 +358,10 @@ class Controller:
         mj.published = doc
         self._event(mj.uid, "MembershipPublished", json.dumps(doc))
         return True
+
+    def _rdzv_path(self, mj: ManagedJob) -> str:
+        port = mj.job.cluster_spec("master", 0)["env"][0]["value"]
+        return os.path.join(self.rdzv_dir, "tok8s-%s-%s" % (mj.job.name.replace("/", "-"), port))
 
     def _start_replica(self, mj: ManagedJob, tt: str, idx: int, restarts: int = 0) -> None:
         spec = mj.job.cluster_spec(tt.lower(), idx)

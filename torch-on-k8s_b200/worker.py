@@ -188,10 +188,16 @@ def init_replica(job_id: Optional[str] = None, *, device: Optional[int] = None,
     rdzv = os.environ.get("TOK8S_RDZV") or default_rendezvous_path(job_id)
     epoch = int(os.environ.get("TOK8S_EPOCH", "0"))
     if epoch > 0:
-        # started into a running job (elastic scale-out): the controller announces the membership
-        # this replica belongs to once every member has a process; join at THAT epoch with the rank /
-        # world it states (a scale-out that was reverted first never lists this replica)
-        rank, world, epoch = wait_for_membership(rdzv, os.environ.get("TOK8S_REPLICA", ""), epoch)
+        # started into a running job (elastic scale-out): tell the controller this replica is up
+        # (process started, CUDA initialised, whatever the script built before calling init_replica),
+        # so that it can announce the new membership only when the survivors will not have to wait
+        # for anybody's start-up; then join at the announced epoch with the rank / world it states
+        # (a scale-out that was reverted first never lists this replica)
+        torch.zeros(1, device=dev)
+        replica = os.environ.get("TOK8S_REPLICA", "")
+        with open("%s.ready.%s" % (rdzv, replica), "w") as f:
+            f.write(str(epoch))
+        rank, world, epoch = wait_for_membership(rdzv, replica, epoch)
     comm = Communicator(job_id, rank, world, device, max_world=max_world, rendezvous_path=rdzv,
                         epoch=epoch)
     return Replica(rank=rank, world=world, device=dev, comm=comm, job_id=job_id)

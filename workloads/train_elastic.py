@@ -65,11 +65,16 @@ def main() -> int:
     from torch_on_k8s_b200.sampler import ReplicaSampler
     from torch_on_k8s_b200.worker import init_replica
 
-    rep = init_replica(bootstrap_backend=None)          # no torch.distributed: the world may change
+    # everything that does not need the peer group first: a replica that joins a running job reports
+    # ready (inside init_replica) only after its model is built, so the survivors never wait for it
+    gpu = int(os.environ.get("TOK8S_GPU", os.environ.get("LOCAL_RANK", os.environ.get("RANK", "0"))))
+    torch.cuda.set_device(gpu)
+    dev = torch.device("cuda", gpu)
+    data_rank = int(os.environ.get("RANK", "0"))
+    model, loss_of, units = build(a.model, a.batch, data_rank, dev)
+    rep = init_replica(bootstrap_backend=None, device=gpu)   # no torch.distributed: the world may change
     joined_at_epoch = rep.comm.caps().epoch
-    dev = rep.device
     name = os.environ.get("TOK8S_REPLICA", "replica-%d" % rep.rank)
-    model, loss_of, units = build(a.model, a.batch, rep.rank, dev)
     edp = ElasticDataParallel(model, rep.comm, bucket_cap_mb=25)
     opt = torch.optim.SGD(model.parameters(), lr=a.lr, momentum=0.9)
     sampler = ReplicaSampler(a.steps * a.batch * 8, rep.world, rep.rank, seed=0)
