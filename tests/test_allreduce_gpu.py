@@ -379,7 +379,8 @@ def test_dead_peer_times_out_instead_of_hanging(tok_lib, symm):
         from torch_on_k8s_b200.elastic_dp import symm_tensor
         x = symm_tensor(comms[0], 4096, torch.float32).fill_(1.0) if symm else \
             torch.ones(4096, device="cuda")
-        comms[0].allreduce_bucket(x, x, scale=0.5)   # rank 1 never calls
+        # (two-shot by name for the pool bucket: AUTO takes one-shot for 16 KiB)
+        comms[0].allreduce_bucket(x, x, scale=0.5, algo=3 if symm else 0)   # rank 1 never calls
         torch.cuda.synchronize()
         with pytest.raises(_ffi.TokError) as e:
             comms[0].status()
@@ -495,7 +496,7 @@ def test_elastic_training_without_torch_distributed(tok_lib, n_gpus):
         ts = [threading.Thread(target=guarded(fn), args=(i,)) for i in ids]
         [t.start() for t in ts]
         [t.join(300) for t in ts]
-        assert not errs, errs[0]
+        assert not errs, "\n=====\n".join(errs)
 
     def make(i, rank, world, epoch):
         torch.cuda.set_device(devs[i])

@@ -52,6 +52,19 @@ def wait_for(pred, ctl, timeout):
     return False
 
 
+def dump(ctl, log_dir):
+    """events + the tail of every replica log, for assertion messages"""
+    out = ["events: %r" % (ctl.events[-12:],)]
+    if os.path.isdir(log_dir):
+        for fn in sorted(os.listdir(log_dir)):
+            try:
+                out.append("---- %s ----\n%s" % (fn, "".join(open(os.path.join(log_dir, fn),
+                                                                   errors="replace").readlines()[-25:])))
+            except OSError:
+                pass
+    return "\n".join(out)
+
+
 def progress(log_dir, replica):
     try:
         lines = open(os.path.join(log_dir, replica + ".log")).read().splitlines()
@@ -75,16 +88,17 @@ def test_controller_rescales_gpu_job_in_place(tok_lib, n_gpus, tmp_path, monkeyp
     ctl = Controller(num_gpus=4, log_dir=logs, rdzv_dir=str(tmp_path), drain_grace_s=60,
                      gpu_map=[i % max(n_gpus, 1) for i in range(4)], wait_ready=True)
     uid = ctl.submit(manifest("el", workers=1))
-    assert wait_for(lambda: progress(logs, "el-master-0") >= 20, ctl, 180), ctl.events[-6:]
+    assert wait_for(lambda: progress(logs, "el-master-0") >= 20, ctl, 180), dump(ctl, logs)
     assert ctl.scale(uid, "Worker", 3) == 1                     # world 2 -> 4
-    assert wait_for(lambda: any(e[2] == "MembershipPublished" for e in ctl.events), ctl, 120)
+    assert wait_for(lambda: any(e[2] == "MembershipPublished" for e in ctl.events), ctl, 120), \
+        dump(ctl, logs)
     at = progress(logs, "el-master-0")
-    assert wait_for(lambda: progress(logs, "el-worker-2") >= at + 30, ctl, 180), ctl.events[-6:]
+    assert wait_for(lambda: progress(logs, "el-worker-2") >= at + 30, ctl, 180), dump(ctl, logs)
     assert ctl.scale(uid, "Worker", 1) == 2                     # world 4 -> 2
     assert wait_for(lambda: sum(e[2] == "SuccessfulDeletePod" for e in ctl.events) == 2, ctl, 120), \
-        ctl.events[-8:]
+        dump(ctl, logs)
     res = ctl.run_until_done(timeout=400)
-    assert res[uid] == "Succeeded", ctl.events[-8:]
+    assert res[uid] == "Succeeded", dump(ctl, logs)
     pods = [e[3] for e in ctl.events if e[2] == "SuccessfulCreatePod"]
     assert pods == ["el-master-0", "el-worker-0", "el-worker-1", "el-worker-2"]   # nobody restarted
     # the scale-out was announced only once both joiners were up: the survivors trained on meanwhile
@@ -134,7 +148,7 @@ def test_two_queued_gpu_jobs_gang_admission_under_wrr(tok_lib, n_gpus, tmp_path,
     a = ctl.submit(manifest("ja", 1, queue="qa", min_members={"Master": 1, "Worker": 1}))
     b = ctl.submit(manifest("jb", 1, queue="qb", min_members={"Master": 1, "Worker": 1}))
     res = ctl.run_until_done(timeout=300)
-    assert res == {a: "Succeeded", b: "Succeeded"}, ctl.events[-8:]
+    assert res == {a: "Succeeded", b: "Succeeded"}, dump(ctl, str(tmp_path / "logs"))
     admitted = [e[1] for e in ctl.events if e[2] == "GangAdmitted"]
     assert sorted(admitted) == sorted([a, b])
     first, second = admitted

@@ -269,15 +269,17 @@ __device__ __forceinline__ int warp_min8(int d) {
 }
 
 // Spin until `*word - want >= 0` on every polling lane.  Returns 0, or the status code to report.
+// `where`: 1 = bucket arrival, 2 = in-kernel CTA barrier (recorded with the lanes that were still
+// behind when the wait was given up, so that tok_comm_status can say WHICH replica is missing).
 __device__ __forceinline__ int warp_spin(const KArgs& a, const uint32_t* word, uint32_t want,
-                                         bool polls) {
+                                         bool polls, uint32_t where) {
   const int lane = threadIdx.x & 31;
   unsigned long long t0 = 0;
   uint32_t spins = 0;
   for (;;) {
-    int d = 0;
-    if (polls) d = static_cast<int32_t>(ld_relaxed_sys(word) - want);
-    d = warp_min8(d);
+    int mine = 0;
+    if (polls) mine = static_cast<int32_t>(ld_relaxed_sys(word) - want);
+    const int d = warp_min8(mine);
     if (d >= 0) return 0;
     if ((++spins & 0xfffu) == 0) {
       int code = 0;
@@ -293,7 +295,15 @@ __device__ __forceinline__ int warp_spin(const KArgs& a, const uint32_t* word, u
         }
       }
       code = __shfl_sync(0xffffffffu, code, 0);
-      if (code) return code;
+      if (code) {
+        const unsigned behind = __ballot_sync(0xffffffffu, polls && mine < 0);
+        if (lane == 0 && a.hostctl[kCtlWhere] == 0) {
+          a.hostctl[kCtlBehind] = behind;
+          a.hostctl[kCtlWant] = want;
+          a.hostctl[kCtlWhere] = where | (blockIdx.x << 8);
+        }
+        return code;
+      }
     }
   }
 }
@@ -320,7 +330,7 @@ __device__ __forceinline__ bool cta_barrier(const KArgs& a, uint32_t target, int
              (blockIdx.x * kMaxWorld + (polls ? lane : 0));
       want = target;
     }
-    const int code = warp_spin(a, word, want, polls);
+    const int code = warp_spin(a, word, want, polls, 2u);
     if (code != 0 && lane == 0) {
       a.hostctl[kCtlStatus] = code;
       *s_fail = 1;
@@ -1002,7 +1012,7 @@ __global__ void __launch_bounds__(32) arrive_kernel(const __grid_constant__ KArg
   }
   const uint32_t* word =
       reinterpret_cast<const uint32_t*>(a.peer[a.rank] + kArrOff) + (polls ? lane : 0);
-  int code = warp_spin(a, word, target, polls);
+  int code = warp_spin(a, word, target, polls, 1u);
   fence_sys();
   if (code == 0 && polls && a.buf_off != 0) {
     const unsigned long long theirs = ld_relaxed_sys(
@@ -1189,7 +1199,9 @@ __global__ void __launch_bounds__(kThreads, 1) bcast_kernel(const __grid_constan
 __global__ void __launch_bounds__(kThreads, 1) barrier_bench_kernel(const __grid_constant__ KArgs a) {
   __shared__ int s_fail;
   const int variant = static_cast<int>(a.flags);
-  const int slot = 128 + blockIdx.x;
+  // the multicast counters (slots 192..255) and the P2P flags (slots 128..191) count separately
+  const bool mc_variant = a.mc != nullptr && (variant == 0 || variant == 2 || variant == 4);
+  const int slot = (mc_variant ? 192 : 128) + blockIdx.x;
   if (threadIdx.x == 0) s_fail = 0;
   uint32_t bar = a.ctr[slot];
   __syncthreads();
@@ -1234,7 +1246,7 @@ __global__ void __launch_bounds__(kThreads, 1) barrier_bench_kernel(const __grid
         word = reinterpret_cast<const uint32_t*>(a.peer[a.rank]) + (slot * kMaxWorld + (polls ? lane : 0));
         want = bar;
       }
-      const int code = warp_spin(a, word, want, polls);
+      const int code = warp_spin(a, word, want, polls, 3u);
       if (code != 0 && lane == 0) {
         a.hostctl[kCtlStatus] = code;
         s_fail = 1;

@@ -814,6 +814,7 @@ int exchange(tok_comm* c) {
   RT_CHECK(cudaDeviceSynchronize());
   c->hostctl[kCtlAbort] = 0;
   c->hostctl[kCtlStatus] = 0;
+  c->hostctl[kCtlWhere] = 0;
   if (c->world > 1) {
     int all_reset = 0;
     rc = star.all_ok(1, &all_reset);
@@ -996,10 +997,15 @@ int tok_comm_abort(tok_comm_t* c) {
 int tok_comm_status(tok_comm_t* c) {
   if (!c || !c->hostctl) return fail(TOK_ERR_INVALID, "comm is null");
   const uint32_t s = c->hostctl[kCtlStatus];
-  if (s == 1)
+  if (s == 1) {
+    const uint32_t where = c->hostctl[kCtlWhere];
     return fail(TOK_ERR_TIMEOUT,
-                "a peer replica never reached the in-kernel barrier within %llu ms (rank %d of %d)",
-                c->barrier_timeout_ns / 1000000ull, c->rank, c->world);
+                "a peer replica never reached the in-kernel barrier within %llu ms (rank %d of %d; "
+                "given up in %s, CTA %u, ranks still behind: mask 0x%x, waited for value %u)",
+                c->barrier_timeout_ns / 1000000ull, c->rank, c->world,
+                (where & 0xff) == 1 ? "the bucket arrival" : (where & 0xff) == 2 ? "a CTA barrier" : "?",
+                where >> 8, c->hostctl[kCtlBehind], c->hostctl[kCtlWant]);
+  }
   if (s == 2) return fail(TOK_ERR_ABORTED, "collective aborted by tok_comm_abort()");
   if (s == 3)
     return fail(TOK_ERR_STATE,

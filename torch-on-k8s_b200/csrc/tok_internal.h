@@ -41,6 +41,11 @@ constexpr int kCtrWords = kMaxCtas + 4;
 // host-mapped control words (one pinned page), index into KArgs::hostctl
 constexpr int kCtlAbort = 0;   // host -> device: leave barriers now
 constexpr int kCtlStatus = 1;  // device -> host: 0 ok, 1 timeout, 2 aborted, 3 asymmetric buffer
+constexpr int kCtlWhere = 2;   // device -> host: where the first wait was given up (1 arrival, 2 CTA
+                               // barrier, 3 barrier bench) | CTA index << 8
+constexpr int kCtlBehind = 3;  // ... bit r set: rank r's flag had not reached the wanted value (P2P
+                               // flags / arrival); bit 0 alone with a multicast counter: the sum
+constexpr int kCtlWant = 4;    // ... the value waited for
 
 // internal algorithm ids (zero-copy variants of the public TOK_ALGO_* ones, and the broadcast modes)
 constexpr int kAlgoTwoShotInplace = 5;
