@@ -293,3 +293,26 @@ def test_full_box_keeps_low_priority_job_queued_so_priority_wins(tok_lib, tmp_pa
     assert set(res.values()) == {"Succeeded"}, res
     order = [e[1] for e in ctl.events if e[2] == "JobDequeued"]
     assert order == [a, c, b]
+
+
+def test_metrics_endpoint_and_replica_telemetry(tok_lib, tmp_path):
+    """f3: the reference's metric names over GET /metrics (main.go:59), and the two new series fed
+    from `TOK8S_METRIC {...}` lines a replica prints (worker.report_metric) — scraped like the
+    torchelastic progress line."""
+    import urllib.request
+    from torch_on_k8s_b200.controller import ManagedJob, ReplicaProc
+    from torch_on_k8s_b200.job import TorchJob
+    ctl = Controller(num_gpus=2)
+    log = tmp_path / "j-master-0.log"
+    log.write_text('noise\nTOK8S_METRIC {"busbw_gbps": 512.5}\nTOK8S_METRIC {"reform_s": 0.25}\nTOK8S_METRIC {"half')
+    job = TorchJob(manifest("j", free_port()))
+    mj = ManagedJob(job=job, uid="default/j")
+    mj.replicas["Master"] = {0: ReplicaProc("Master", 0, 0, log_path=str(log))}
+    ctl._scrape_metrics(mj)
+    ctl._scrape_metrics(mj)                       # nothing is counted twice; the partial line waits
+    port = free_port()
+    ctl.metrics.serve(port)
+    text = urllib.request.urlopen("http://127.0.0.1:%d/metrics" % port, timeout=10).read().decode()
+    assert 'torch_on_k8s_allreduce_busbw_gbps{job="j"} 512.5' in text
+    assert 'torch_on_k8s_reform_latency_seconds_count{job="j"} 1.0' in text
+    assert "torch_on_k8s_jobs_created_total" in text and "torch_on_k8s_tenant_queue_jobs_pending_count" in text

@@ -52,6 +52,7 @@ class ReplicaProc:
     restarts: int = 0
     log_path: Optional[str] = None
     epoch: int = 0              # membership epoch at which this replica was started
+    log_pos: int = 0            # bytes of the log already scraped for TOK8S_METRIC records
 
 
 @dataclass
@@ -185,6 +186,7 @@ class Controller:
         restarting = self._poll(mj)
         if restarting:
             mj.retries += 1
+        self._scrape_metrics(mj)
         # termination policies first, as ReconcileJobs does (controllers/common/job.go:100-200)
         pods = {tt: [dict(phase=r.phase, restartCount=r.restarts) for r in v.values()]
                 for tt, v in mj.replicas.items()}
@@ -247,6 +249,28 @@ class Controller:
         if last in ("Failed", "Succeeded"):
             term = job.check_termination(pods, mj.retries, _now())
             self._finish(mj, term.get("deletePods", "None"))
+
+    def _scrape_metrics(self, mj: ManagedJob) -> None:
+        """New `TOK8S_METRIC {...}` lines of the master / first worker log -> Prometheus series."""
+        import json
+        for tt in ("Master", "Worker"):
+            r = mj.replicas.get(tt, {}).get(0)
+            if r is None or not r.log_path:
+                continue
+            try:
+                with open(r.log_path, "rb") as f:
+                    f.seek(r.log_pos)
+                    chunk = f.read()
+            except OSError:
+                continue
+            cut = chunk.rfind(b"\n") + 1          # only whole lines
+            r.log_pos += cut
+            for ln in chunk[:cut].decode("utf-8", "replace").splitlines():
+                if ln.startswith("TOK8S_METRIC "):
+                    try:
+                        self.metrics.feed(mj.job.name, json.loads(ln[13:]))
+                    except ValueError:
+                        pass
 
     # ---- torchelastic (controllers/train/torchelastic/elastictorchjob_controller.go:142-166) -------
     def _elastic_pass(self, mj: ManagedJob) -> None:
@@ -512,8 +536,12 @@ def main(argv=None) -> int:
     ap.add_argument("--log-dir", default=None)
     ap.add_argument("--state-dir", default=os.environ.get("TOK8S_STATE_DIR"))
     ap.add_argument("--timeout", type=float, default=3600)
+    ap.add_argument("--metrics-port", type=int, default=0,
+                    help="serve GET /metrics here (the reference's default is 8443; 0 = off)")
     a = ap.parse_args(argv)
     ctl = Controller(a.gpus, policy=a.policy, log_dir=a.log_dir, state_dir=a.state_dir)
+    if a.metrics_port:
+        ctl.metrics.serve(a.metrics_port)
     for m in a.manifests:
         ctl.submit(load_manifest(m), shlex.split(a.command) if a.command else None)
     res = ctl.run_until_done(a.timeout)

@@ -48,3 +48,17 @@ class Metrics:
 
     def render(self) -> str:
         return generate_latest(self.registry).decode()
+
+    def serve(self, port: int = 8443, addr: str = "127.0.0.1"):
+        """GET /metrics on the reference's default port (main.go:59 `--metrics-addr 8443`,
+        metrics.StartMonitoringForDefaultRegistry).  Returns (server, thread)."""
+        from prometheus_client import start_http_server
+        return start_http_server(port, addr=addr, registry=self.registry)
+
+    def feed(self, job: str, record: dict) -> None:
+        """One `TOK8S_METRIC {...}` record printed by a replica (worker.report_metric): the two
+        series of the new path."""
+        if "busbw_gbps" in record:
+            self.busbw.labels(job).set(float(record["busbw_gbps"]))
+        if "reform_s" in record:
+            self.reform_latency.labels(job).observe(float(record["reform_s"]))

@@ -153,6 +153,15 @@ class Replica:
             dist.destroy_process_group()
 
 
+def report_metric(**record) -> None:
+    """Replica -> controller telemetry over the one channel a pod always has, its log: the controller
+    scrapes `TOK8S_METRIC {...}` lines (as the reference scrapes the torchelastic progress line,
+    controllers/train/torchelastic/observation.go:40-85) into the Prometheus series
+    torch_on_k8s_allreduce_busbw_gbps / torch_on_k8s_reform_latency_seconds."""
+    import json
+    print("TOK8S_METRIC " + json.dumps(record), flush=True)
+
+
 def membership_update(doc: dict, replica_name: str, current_epoch: int):
     """Pure decision behind Replica.poll_membership: (new_world, new_rank, member_mask, epoch) for
     tok_comm_reform, or None when the published epoch is not newer / this replica was dropped."""

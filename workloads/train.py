@@ -39,14 +39,14 @@ def main() -> int:
 
     import torch
     from torch_on_k8s_b200.sampler import ReplicaSampler
-    from torch_on_k8s_b200.worker import init_replica
+    from torch_on_k8s_b200.worker import init_replica, report_metric
 
     rep = init_replica()
     model, shape, classes, dtype = build(a.model)
     model = model.to(rep.device).to(dtype)
     if len(shape) == 3:
         model = model.to(memory_format=torch.channels_last)
-    ddp, _ = rep.wrap(model)
+    ddp, hook = rep.wrap(model, record_events=(rep.rank == 0))
     opt = torch.optim.SGD(ddp.parameters(), lr=0.01, momentum=0.9)
     sampler = ReplicaSampler(a.steps * a.batch * rep.world, rep.world, rep.rank, seed=0)
     gen = torch.Generator(device=rep.device).manual_seed(1234 + rep.rank)
@@ -70,6 +70,12 @@ def main() -> int:
             print("Epoch: [0][%4d/%d]\tTime %6.3f (%6.3f)\tData  0.000 ( 0.000)\tLoss %.4e\t"
                   "Acc@1 %6.2f (%6.2f)\tAcc@5 %6.2f (%6.2f)" %
                   (step + 1, a.steps, lat, lat, float(loss), acc, acc, acc, acc), flush=True)
+            if rep.rank == 0 and rep.world > 1:
+                ev = hook.drain_events()       # [(wire bytes, bucket bytes, exchange ms, wait ms)]
+                ms = sum(e[2] for e in ev)
+                if ms > 0:                      # nccl-tests convention: S/t * 2(N-1)/N
+                    report_metric(busbw_gbps=sum(e[0] for e in ev) / (ms * 1e-3) / 1e9 *
+                                  2.0 * (rep.world - 1) / rep.world)
     torch.cuda.synchronize()
     rep.comm.status()
     rep.close()

@@ -63,7 +63,7 @@ def main() -> int:
     import torch
     from torch_on_k8s_b200.elastic_dp import ElasticDataParallel
     from torch_on_k8s_b200.sampler import ReplicaSampler
-    from torch_on_k8s_b200.worker import init_replica
+    from torch_on_k8s_b200.worker import init_replica, report_metric
 
     # everything that does not need the peer group first: a replica that joins a running job reports
     # ready (inside init_replica) only after its model is built, so the survivors never wait for it
@@ -113,6 +113,8 @@ def main() -> int:
             step, sync_s = hand_over(step)
             log(event="reformed", epoch=rep.comm.caps().epoch, step=step, sync_s=sync_s,
                 reform_visible_s=time.time() - t0)
+            if rep.rank == 0:
+                report_metric(reform_s=time.time() - t0)
             t_prev = time.time()
         edp.zero_grad()
         loss = loss_of(edp)
