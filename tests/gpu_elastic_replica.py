@@ -46,12 +46,15 @@ def digest():
 
 import time  # noqa: E402
 step = 0
+fresh = False
 if rep.comm.caps().epoch > 0:
     step = hand_over(0)
+    fresh = True      # the survivors go straight from the hand-over to the training step: so do we
     history.append(dict(event="joined", step=step, world=rep.world, rank=rep.rank,
                         epoch=rep.comm.caps().epoch))
 while step < steps:
-    upd = rep.poll_membership_collective()
+    upd = None if fresh else rep.poll_membership_collective()
+    fresh = False
     if upd is not None:
         if upd[0] == "dropped":
             history.append(dict(event="dropped", step=step))

@@ -815,10 +815,33 @@ int exchange(tok_comm* c) {
   c->hostctl[kCtlAbort] = 0;
   c->hostctl[kCtlStatus] = 0;
   c->hostctl[kCtlWhere] = 0;
+  // identity token at the end of the control page: after the host barrier every replica reads every
+  // peer's token THROUGH ITS PEER MAPPING and compares it with the uid the membership table lists for
+  // that rank — a wrong or stale mapping fails here, loudly, instead of as a silent hang later
+  RT_CHECK(cudaMemcpy(reinterpret_cast<char*>(c->local_va) + kTokenOff, &c->uid, sizeof(c->uid),
+                      cudaMemcpyHostToDevice));
+  RT_CHECK(cudaDeviceSynchronize());
   if (c->world > 1) {
     int all_reset = 0;
     rc = star.all_ok(1, &all_reset);
     if (rc != TOK_OK) return rc;
+    int good = 1;
+    for (int r = 0; r < c->world; ++r) {
+      uint64_t seen = 0;
+      if (cudaMemcpy(&seen, c->peer[r] + kTokenOff, sizeof(seen), cudaMemcpyDeviceToHost) != cudaSuccess ||
+          seen != table[r].uid) {
+        set_error("peer mapping check failed: rank %d's heap as mapped by rank %d carries token %llx, "
+                  "the membership table says %llx",
+                  r, c->rank, (unsigned long long)seen, (unsigned long long)table[r].uid);
+        cudaGetLastError();
+        good = 0;
+      }
+    }
+    int all_good = 0;
+    rc = star.all_ok(good, &all_good);
+    if (rc != TOK_OK) return rc;
+    if (!good) return TOK_ERR_STATE;
+    if (!all_good) return fail(TOK_ERR_STATE, "a peer's mapping check failed");
   }
   return TOK_OK;
 }

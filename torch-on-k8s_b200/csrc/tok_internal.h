@@ -30,6 +30,7 @@ constexpr size_t kFlagBytes = 2u << 20;  // one 2 MiB page: keeps staging 2 MiB 
 constexpr size_t kMcntOff = 16u << 10;
 constexpr size_t kArrOff = 32u << 10;
 constexpr size_t kArrSymOff = (32u << 10) + 64;
+constexpr size_t kTokenOff = (2u << 20) - 64;  // u64 identity token (the owner's uid), checked at rendezvous
 
 // local (non-shared) device words, index into KArgs::ctr
 constexpr int kCtrCallSeq = kMaxCtas;      // number of completed collective launches

@@ -95,14 +95,17 @@ def main() -> int:
         return int(cell[0].item()), time.time() - t0
 
     step = 0
+    fresh = False
     if joined_at_epoch > 0:
         step, sync_s = hand_over(0)
+        fresh = True   # the survivors go straight from the hand-over to the training step: so do we
         log(event="joined", epoch=joined_at_epoch, step=step, startup_s=time.time() - t_proc,
             sync_s=sync_s)
     t_prev = time.time()
     lat_acc = []
     while step < a.steps:
-        upd = rep.poll_membership_collective()
+        upd = None if fresh else rep.poll_membership_collective()
+        fresh = False
         if upd is not None:
             if upd[0] == "dropped":
                 log(event="dropped", step=step)
