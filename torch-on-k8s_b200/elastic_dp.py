@@ -43,7 +43,7 @@ def symm_tensor(comm: Communicator, numel: int, dtype: torch.dtype) -> torch.Ten
 
 
 @torch.no_grad()
-def broadcast_coalesced(comm: Communicator, tensors, root: int = 0) -> None:
+def broadcast_coalesced(comm: Communicator, tensors, root: int = 0, use_pool: bool = True) -> None:
     """Replicate `root`'s `tensors` (one dtype, same device) into every replica's, bit for bit: packed
     into one flat buffer, one tok_broadcast, unpacked in place on the receivers.  The flat buffer is
     taken from the symmetric pool when it fits — the root then feeds all receivers with ONE
@@ -55,7 +55,7 @@ def broadcast_coalesced(comm: Communicator, tensors, root: int = 0) -> None:
     esz = tensors[0].element_size()
     n_pad = (n * esz + 15) // 16 * 16 // esz
     ptr = C.c_void_p()
-    pooled = lib().tok_comm_symm_alloc(comm._h, n_pad * esz, C.byref(ptr)) == 0
+    pooled = use_pool and lib().tok_comm_symm_alloc(comm._h, n_pad * esz, C.byref(ptr)) == 0
     if pooled:
         raw = torch.as_tensor(_RawCuda(ptr.value, n_pad * esz), device=dev)
         flat = raw.view(dtype)
@@ -101,11 +101,12 @@ def bucket_assignment(sizes_bytes, keys, caps):
 
 class ElasticDataParallel(torch.nn.Module):
     def __init__(self, module: torch.nn.Module, comm: Communicator, *, bucket_cap_mb: int = 25,
-                 first_bucket_mb: int = 1, algo: int = 0):
+                 first_bucket_mb: int = 1, algo: int = 0, pool_broadcast: bool = True):
         super().__init__()
         self.module = module
         self.comm = comm
         self.algo = algo
+        self.pool_broadcast = pool_broadcast   # state hand-over through pool buffers (zero-copy path)
         self.buckets: List[torch.Tensor] = []
         self._assign(bucket_cap_mb << 20, first_bucket_mb << 20)
 
@@ -154,7 +155,7 @@ class ElasticDataParallel(torch.nn.Module):
             n = sum(t.numel() for t in ts)
             if n == 0:
                 continue
-            broadcast_coalesced(self.comm, ts, root)
+            broadcast_coalesced(self.comm, ts, root, use_pool=self.pool_broadcast)
 
     @torch.no_grad()
     def sync_params(self, root: int = 0) -> None:
