@@ -201,6 +201,10 @@ int tok_comm_debug_read(tok_comm_t* comm, uint64_t* out, size_t words);
  * 4 = production barrier behind a 64 KiB tail of posted peer stores) — tools/barrier_bench.py.    */
 int tok_comm_debug_barrier(tok_comm_t* comm, int variant, int ctas, size_t count, void* cuda_stream);
 
+/* Debugging aid: `words` u32 of rank `rank`'s control page (barrier / arrival flags), read through
+ * THIS replica's mapping of that heap.                                                           */
+int tok_comm_debug_peek(tok_comm_t* comm, int rank, size_t byte_off, uint32_t* out, size_t words);
+
 /* ---- control plane (TorchJob surface) ------------------------------------------------------
  * JSON in, JSON out.  `tok_job_t` is a parsed + defaulted TorchJob (apis/train/v1alpha1).        */
 

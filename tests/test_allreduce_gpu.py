@@ -125,21 +125,23 @@ def test_exact_patterns_full_resnet_buckets(tok_lib, n_gpus):
 
 def test_golden_gloo_vectors(tok_lib, n_gpus):
     """The committed gloo fixtures (tests/golden/allreduce_gloo_n*.npz): our CUDA result on the same
-    inputs vs what the reference-style gloo job produced."""
+    inputs vs what the reference-style gloo job produced — through the staged kernels (replicas as
+    threads) and through the zero-copy path DDP's buckets take (replicas as processes: the
+    arrival + exchange pair needs one CUDA context per replica)."""
     import torch
     from oracle import allreduce_oracle as O
     from torch_on_k8s_b200.comm import Communicator
-    from torch_on_k8s_b200.elastic_dp import symm_tensor
     gold_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
     import tempfile
     import threading
     for world in (2, 4, 8):
-        with np.load(os.path.join(gold_dir, "allreduce_gloo_n%d.npz" % world)) as z:
+        gpath = os.path.join(gold_dir, "allreduce_gloo_n%d.npz" % world)
+        with np.load(gpath) as z:
             g = {k: z[k] for k in z.files}  # NpzFile is not thread-safe: materialise first
         devs, env = devices_for(world, n_gpus)
         os.environ.update(env or SHARED_ENV)
         path = os.path.join(tempfile.mkdtemp(prefix="tok8s-gold-"), "r")
-        outs, zouts, errs = {}, {}, []
+        outs, errs = {}, []
 
         def body(r):
             try:
@@ -149,24 +151,11 @@ def test_golden_gloo_vectors(tok_lib, n_gpus):
                 with torch.cuda.stream(st):
                     x = torch.from_numpy(g["randn_x32_r%d" % r].copy()).to("cuda:%d" % devs[r])
                     xb = harness.to_torch(g["randn_xb_r%d" % r], "bf16", "cuda:%d" % devs[r])
-                    # the zero-copy path DDP's buckets take: same inputs, in the symmetric pool
-                    n32 = (x.numel() // 4) * 4
-                    nb = (xb.numel() // 8) * 8
-                    # (direct pool allocation: a MemPool serves one communicator per process, and
-                    # these replicas are threads of one process)
-                    zx = symm_tensor(comm, n32, torch.float32).copy_(x[:n32])
-                    zb = symm_tensor(comm, nb, torch.bfloat16).copy_(xb[:nb])
                     comm.allreduce_bucket(x, x, scale=1.0 / world, stream=st)
                     comm.allreduce_bucket(xb, xb, scale=1.0 / world, stream=st)
-                    # (two-shot asked for by name: AUTO would take one-shot for buckets this small)
-                    comm.allreduce_bucket(zx, zx, scale=1.0 / world, algo=3, stream=st)
-                    kz = comm.last_algo()
-                    comm.allreduce_bucket(zb, zb, scale=1.0 / world, algo=3, stream=st)
                     st.synchronize()
                 comm.status()
-                assert kz in ("two_shot_inplace", "nvls_inplace"), kz
                 outs[r] = (x.cpu().numpy(), harness.from_torch(xb, "bf16"))
-                zouts[r] = (zx.cpu().numpy(), harness.from_torch(zb, "bf16"), kz)
                 comm.close()
             except Exception as e:  # noqa: BLE001
                 errs.append(repr(e))
@@ -186,17 +175,14 @@ def test_golden_gloo_vectors(tok_lib, n_gpus):
             ulp = O.ulp_distance(gotb, wantb, "bf16")
             assert ulp.max() <= 1 and (ulp != 0).mean() < 0.01, (world, r)
             assert np.array_equal(outs[0][0].view(np.uint32), got32.view(np.uint32))
-            # zero-copy: the P2P in-place kernel is the staged result bit for bit; the in-switch sum
-            # (NVLS, one GPU per replica) is held to the gloo goldens by the north_star tolerance
-            z32, zb, kz = zouts[r]
-            n32, nb = z32.size, zb.size
-            if kz == "two_shot_inplace":
-                assert np.array_equal(z32.view(np.uint32), got32[:n32].view(np.uint32)), (world, r)
-                assert np.array_equal(zb, gotb[:nb]), (world, r)
-            errz = np.abs(z32.astype(np.float64) - want[:n32].astype(np.float64)).max()
-            assert errz / np.abs(want).max() <= 1e-5, (world, r, kz)
-            ulpz = O.ulp_distance(zb, wantb[:nb], "bf16")
-            assert ulpz.max() <= 1, (world, r, kz)
+        # zero-copy: the same fixtures through pool buckets (P2P in place; NVLS in place when every
+        # replica has its own GPU and the group has >= 2 of them)
+        cases = [dict(golden=gpath, algo=3, count=0, **{"in": "f32", "wire": "f32", "out": "f32"})]
+        if n_gpus >= world:
+            cases.append(dict(golden=gpath, algo=4, count=0, **{"in": "f32", "wire": "f32", "out": "f32"}))
+        res = harness.launch(world, cases, devices=devs, mode="proc", timeout=600, env=env)
+        s = harness.summarize(res)
+        assert s["bad"] == 0 and s["total"] == len(cases) * world, s
 
 
 @pytest.mark.parametrize("world", [2, 3, 4])
@@ -475,6 +461,13 @@ def test_elastic_training_without_torch_distributed(tok_lib, n_gpus):
     from torch_on_k8s_b200.elastic_dp import ElasticDataParallel
     from workloads.mlp import batch, mlp
     os.environ.update(SHARED_ENV)
+    # Replicas are THREADS of this process here.  The zero-copy exchange is a pair of kernels per
+    # bucket (1-warp arrival, then the exchange): inside ONE CUDA context the exchange kernel queued
+    # behind a waiting arrival blocks the context's work queue, a peer's arrival enqueued later is
+    # never dispatched, and both time out (tools/thread_arrival_diag.py).  One context per replica —
+    # processes, the product shape — is what tests/test_controller_gpu.py runs the zero-copy + re-form
+    # combination in; this test keeps the pool buckets but exchanges them with the staged kernels.
+    os.environ["TOK_DISABLE_ZERO_COPY"] = "1"
     path = os.path.join(tempfile.mkdtemp(prefix="tok8s-edp-"), "r")
     devs = list(range(4)) if n_gpus >= 4 else [0] * 4
     state, errs = {}, []
@@ -506,11 +499,6 @@ def test_elastic_training_without_torch_distributed(tok_lib, n_gpus):
             with init_lock:
                 model = mlp(seed=0 if epoch == 0 else 100 + i)   # joiners start "wrong"
             model = model.cuda(devs[i])
-            # KNOWN ISSUE: with replicas that are THREADS of one process (one CUDA
-            # context, every heap aliased several times in one address space) the first bucket
-            # arrival after a re-form can leave one replica deaf to its peers' arrival flags; replicas
-            # that are processes — the product shape, tests/test_controller_gpu.py — are unaffected.
-            # The hand-over therefore goes through the staged broadcast here.
             edp = ElasticDataParallel(model, comm, algo=3, pool_broadcast=False)
             x, y = batch(i, 64)
             state[i] = dict(comm=comm, edp=edp, x=x.cuda(devs[i]), y=y.cuda(devs[i]), stream=st,
@@ -571,5 +559,6 @@ def test_elastic_training_without_torch_distributed(tok_lib, n_gpus):
     run_all(lambda i: state[i]["edp"].reform(2, keep.index(i), 0b0101, 2), keep)
     step(keep, "w2c")
     assert state[0]["comm"].caps().epoch == 2
+    os.environ.pop("TOK_DISABLE_ZERO_COPY", None)
     for s in state.values():
         s["comm"].close()

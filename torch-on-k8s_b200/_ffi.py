@@ -114,6 +114,7 @@ PROTOTYPES = {
     "tok_comm_use_as_pool": (C.c_int, [_P]),
     "tok_pool_malloc": (C.c_void_p, [C.c_ssize_t, C.c_int, _P]),
     "tok_pool_free": (None, [_P, C.c_size_t, C.c_int, _P]),
+    "tok_comm_debug_peek": (C.c_int, [_P, C.c_int, C.c_size_t, C.POINTER(C.c_uint32), C.c_size_t]),
     "tok_comm_debug_barrier": (C.c_int, [_P, C.c_int, C.c_int, C.c_size_t, _P]),
     "tok_comm_debug_read": (C.c_int, [_P, C.POINTER(C.c_uint64), C.c_size_t]),
     "tok_set_feature_gates": (C.c_int, [C.c_uint]),

@@ -997,11 +997,12 @@ __global__ void __launch_bounds__(kThreads, 1) nvls_kernel(const __grid_constant
 // which therefore needs no leading barrier.  While a replica waits for the slowest peer's backward
 // it occupies one warp instead of a whole exchange grid.  Zero-copy symmetry check rides along: each
 // replica announces the heap offset of its bucket (buf_off != 0) and compares.
+// Constraint (measured, tools/thread_arrival_diag.py): replicas must not share a CUDA context.  With
+// replicas as THREADS of one process, the exchange kernel queued behind a waiting arrival blocks the
+// context's work queue, a peer's arrival enqueued later is never dispatched, and both sides time out.
+// One process per replica — the product shape — has one context each.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(32) arrive_kernel(const __grid_constant__ KArgs a) {
-  // programmatic dependent launch: an exchange kernel launched behind this one with the PDL attribute
-  // may become resident now; it parks in griddepcontrol.wait until this grid has completed
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int lane = threadIdx.x;
   const uint32_t target = a.ctr[kCtrArrive] + 1;
   const bool polls = lane < a.world;
@@ -1042,7 +1043,6 @@ __global__ void __launch_bounds__(kThreads, 1) nvls_inplace_kernel(const __grid_
   using A = AR<WIRE, WIRE, WIRE>;
   __shared__ uint32_t s_words[3];
   __shared__ int s_fail;
-  asm volatile("griddepcontrol.wait;" ::: "memory");  // no-op unless launched with the PDL attribute
   CtaState st = cta_begin(a, s_words, &s_fail);
   const size_t lo = static_cast<size_t>(blockIdx.x) * a.packs_per_cta;
   const size_t hi = min_sz(lo + a.packs_per_cta, a.total_packs);
@@ -1070,7 +1070,6 @@ __global__ void __launch_bounds__(kThreads, 1)
   using A = AR<WIRE, WIRE, WIRE>;
   __shared__ uint32_t s_words[3];
   __shared__ int s_fail;
-  asm volatile("griddepcontrol.wait;" ::: "memory");  // no-op unless launched with the PDL attribute
   CtaState st = cta_begin(a, s_words, &s_fail);
   const float pre = (a.flags & TOK_FLAG_SCALE_POST) ? 1.f : a.scale;
   const float post = (a.flags & TOK_FLAG_SCALE_POST) ? a.scale : 1.f;
@@ -1292,27 +1291,10 @@ int launch_typed(int algo, int ctas, const KArgs& a, cudaStream_t s) {
     case kAlgoTwoShotInplace:
     case kAlgoNvlsInplace:
       if constexpr (std::is_same<IN, WIRE>::value && std::is_same<WIRE, OUT>::value) {
-        // a.root doubles as the PDL switch for these kernels (it is only meaningful for broadcast):
-        // launched with programmatic stream serialization the CTAs become resident while the arrival
-        // kernel in front is still waiting and start the moment it completes
-        cudaLaunchConfig_t cfg;
-        memset(&cfg, 0, sizeof(cfg));
-        cfg.gridDim = dim3(ctas);
-        cfg.blockDim = dim3(kThreads);
-        cfg.stream = s;
-        cudaLaunchAttribute attr;
-        attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr.val.programmaticStreamSerializationAllowed = 1;
-        if (a.root == 1) {
-          cfg.attrs = &attr;
-          cfg.numAttrs = 1;
-        }
-        cudaError_t le;
         if (algo == kAlgoNvlsInplace)
-          le = cudaLaunchKernelEx(&cfg, nvls_inplace_kernel<WIRE>, a);
+          nvls_inplace_kernel<WIRE><<<ctas, kThreads, 0, s>>>(a);
         else
-          le = cudaLaunchKernelEx(&cfg, two_shot_inplace_kernel<WIRE>, a);
-        if (le != cudaSuccess) return static_cast<int>(le);
+          two_shot_inplace_kernel<WIRE><<<ctas, kThreads, 0, s>>>(a);
         break;
       }
       return static_cast<int>(cudaErrorInvalidValue);

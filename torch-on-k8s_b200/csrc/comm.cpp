@@ -374,7 +374,6 @@ struct tok_comm {
   unsigned long long barrier_timeout_ns = 600000ull * 1000000ull;
   double rdzv_timeout_s = 120;
   int local_tma = 1;        // world 1, one dtype: 1 = cp.async.bulk variant, 0 = LDG.128 wave
-  int pdl = 0;              // zero-copy exchange kernels use programmatic dependent launch
 
   std::atomic<uint64_t> launches{0};    // exchange / broadcast / local kernels
   std::atomic<uint64_t> arrivals{0};    // arrive kernels
@@ -898,7 +897,6 @@ int create_impl(const char* job_id, int rank, int world, int max_world, int devi
   // every size from 4 MB to 1 GiB (12.4 vs 14.5 us at the 28 MB DDP bucket, 0.97 vs 0.71-0.90 of the
   // measured HBM peak at 1 GiB)
   c->local_tma = static_cast<int>(env_size("TOK_LOCAL_TMA", 1));
-  c->pdl = static_cast<int>(env_size("TOK_PDL", 0));
   c->rdzv_timeout_s = static_cast<double>(env_size("TOK_RDZV_TIMEOUT_S", 120));
 
   int rc = TOK_OK;
@@ -1406,7 +1404,6 @@ int tok_allreduce_bucket(tok_comm_t* c, const void* in, void* out, size_t count,
   a.buf_off = pl.buf_off;
   a.scale = scale;
   a.flags = flags & TOK_FLAG_SCALE_POST;
-  a.root = (inplace && c->pdl) ? 1 : 0;  // PDL switch of the zero-copy kernels
 
   for (size_t off = 0; off < count; off += launch_cap) {
     const size_t n = std::min(launch_cap, count - off);
@@ -1458,6 +1455,15 @@ int tok_allreduce_bucket(tok_comm_t* c, const void* in, void* out, size_t count,
     c->last_algo.store(algo);
     c->last_ctas.store(ctas);
   }
+  return TOK_OK;
+}
+
+int tok_comm_debug_peek(tok_comm_t* c, int rank, size_t byte_off, uint32_t* out, size_t words) {
+  if (!c || !out) return fail(TOK_ERR_INVALID, "comm / out is null");
+  if (rank < 0 || rank >= c->world || byte_off + words * 4 > kFlagBytes)
+    return fail(TOK_ERR_INVALID, "rank / offset out of range");
+  DeviceGuard guard(c->device);
+  RT_CHECK(cudaMemcpy(out, c->peer[rank] + byte_off, words * 4, cudaMemcpyDeviceToHost));
   return TOK_OK;
 }
 
