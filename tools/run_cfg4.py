@@ -5,8 +5,8 @@ worth of free GPUs.
   python tools/run_cfg4.py [--out gpurun_out/cfg4.json]
 
 Jobs: resnet50 (queue team-a, 1 master + 3 workers, DDP over libtok8s' comm hook), bert-base (queue
-team-b, 1 + 3, ElasticDataParallel), resnet50-late (queue team-a, 1 + 3, submitted at the same time:
-the box has 8 slots, so it stays queued until a gang of 4 is free).  Recorded: coordinator dequeue
+team-b, 1 + 3, ElasticDataParallel), and — submitted once both are admitted — resnet50-late (queue
+team-a, 1 + 3): the box has 8 slots, so it stays queued until a gang of 4 is free.  Recorded: coordinator dequeue
 order and times (WRR over the two queues, one dequeue per 100 ms tick), gang admissions, queue waits,
 and each job's throughput from its own progress lines.  Measurement harness, not product.
 """
@@ -54,8 +54,15 @@ def main():
             "--steps", str(a.bert_steps)]
     t0 = time.time()
     uids = {"resnet50": ctl.submit(job("resnet50", "team-a", resnet)),
-            "bert-base": ctl.submit(job("bert-base", "team-b", bert)),
-            "resnet50-late": ctl.submit(job("resnet50-late", "team-a", resnet))}
+            "bert-base": ctl.submit(job("bert-base", "team-b", bert))}
+    # the two jobs of the config first: WRR hands out one dequeue per 100 ms tick, alternating the
+    # queues; both gangs fit (4 + 4 of 8 slots).  Once both are admitted a third job joins team-a's
+    # queue: no gang's worth of GPUs is free, so it is held until one of the two finishes.
+    t_wait = time.time()
+    while time.time() - t_wait < 60 and sum(e[2] == "GangAdmitted" for e in ctl.events) < 2:
+        ctl.tick()
+        time.sleep(0.02)
+    uids["resnet50-late"] = ctl.submit(job("resnet50-late", "team-a", resnet))
     res = ctl.run_until_done(timeout=1500)
     ev = ctl.events
 

@@ -22,12 +22,15 @@ def main():
     st = torch.cuda.Stream()
     out = []
     sizes = [22857856, 28256208]
-    for ctas in [int(x) for x in os.environ.get("CTAS", "8,16,32,64").split(",")]:
+    configs = [(int(c), int(u)) for c in os.environ.get("CTAS", "8,16,32,64").split(",")
+               for u in os.environ.get("UNROLL", "8").split(",")]
+    for ctas, unroll in configs:
         os.environ["TOK_ZC_CTAS"] = str(ctas)
+        os.environ["TOK_NVLS_UNROLL"] = str(unroll)
         comm = Communicator("zctune", rank, world, local,
-                            rendezvous_path="/tmp/tok8s-zct-%s-%d" % (os.environ["MASTER_PORT"], ctas))
+                            rendezvous_path="/tmp/tok8s-zct-%s-%d-%d" % (os.environ["MASTER_PORT"], ctas, unroll))
         sets = [[comm.symm_empty(sz // 2, torch.bfloat16).normal_() for sz in sizes] for _ in range(4)]
-        for algo, name in ((0, "auto"), (3, "two_shot_inplace")):
+        for algo, name in [(0, "auto")] + ([(3, "two_shot_inplace")] if os.environ.get("TWO_SHOT") else []):
             with torch.cuda.stream(st):
                 def run(i):
                     for t in sets[i % 4]:
@@ -47,7 +50,7 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             us = float(t.item())
             busbw = (sum(sizes) / 2) / (us * 1e-6) / 1e9 * 2 * (world - 1) / world
-            row = dict(world=world, zc_ctas=ctas, algo=name, kernel=comm.last_algo(),
+            row = dict(world=world, zc_ctas=ctas, nvls_unroll=unroll, algo=name, kernel=comm.last_algo(),
                        us_per_bucket=round(us, 2), busbw_gbs=round(busbw, 1), frac_of_900=round(busbw / 900, 3))
             out.append(row)
             if rank == 0:
@@ -56,8 +59,11 @@ def main():
         comm.close()
         dist.barrier()
     if rank == 0:
-        with open(os.path.join(ROOT, "gpurun_out", "zc_tune_n%d.json" % world), "w") as f:
+        with open(os.path.join(ROOT, "gpurun_out", os.environ.get("OUT", "zc_tune_n%d.json" % world)), "w") as f:
             json.dump(out, f, indent=1)
+        best = min((r for r in out if r["algo"] == "auto"), key=lambda r: r["us_per_bucket"])
+        with open(os.path.join(ROOT, "gpurun_out", "zc_best.env"), "w") as f:
+            f.write("export TOK_ZC_CTAS=%d TOK_NVLS_UNROLL=%d\n" % (best["zc_ctas"], best["nvls_unroll"]))
     dist.destroy_process_group()
 
 

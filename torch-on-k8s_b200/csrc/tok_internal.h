@@ -75,6 +75,7 @@ struct KArgs {
   int rank;
   int world;
   int root;                // broadcast root
+  int unroll;              // NVLS in place: multimem.ld_reduce requests in flight per thread (8 or 16)
   uint32_t flags;          // TOK_FLAG_SCALE_POST
 };
 
