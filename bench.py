@@ -426,6 +426,10 @@ def run_ours(args):
                 "arrival_wait_us": wait_ms_max * 1e3 / n_launch,
                 "peak_source": "nominal NVLink5 900 GB/s per direction (BASELINE.md §2); measured "
                                "peer copy on this pool is 770 GB/s",
+                "traffic_note": "ncu cannot replay a kernel that waits for peer replicas' kernels, so "
+                                "there is no dram__bytes capture for the cross-GPU kernels; the "
+                                "zero-copy exchange makes no staging pass by construction (reads of "
+                                "the bucket by the switch / peers + one write of the result)",
                 "note": "busbw = S/t * 2(N-1)/N over the exchange kernels inside the timed steps, "
                         "concurrent with backward; the wait for the slowest replica is the 1-warp "
                         "arrival kernel in front (arrival_wait_us), not part of t; NVLS may exceed 1.0"}

@@ -306,7 +306,7 @@ def test_nvls_tolerance(tok_lib, n_gpus):
                               expect_kernel="nvls_inplace"))
     # what DDP's buckets take in bench.py: AUTO on pool buckets of the real ResNet-50 sizes, 1/N PRE
     pow2 = world & (world - 1) == 0
-    auto_kernel = "nvls_inplace" if (world >= 3 and pow2) else "two_shot_inplace"
+    auto_kernel = "nvls_inplace" if (world >= 5 and pow2) else "two_shot_inplace"   # 3-4: P2P past 12 MiB
     exact_ids = set()
     for i, nbytes in enumerate((28256208, 22857856)):
         cases.append(dict(count=nbytes // 2, **{"in": "bf16", "wire": "bf16", "out": "bf16"}, algo=0,

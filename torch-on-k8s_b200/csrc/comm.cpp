@@ -1307,7 +1307,10 @@ int plan_bucket(const tok_comm* c, const void* in, const void* out, size_t count
     // in-place kernel, which applies PRE exactly as the staged path does.
     const bool post = (flags & TOK_FLAG_SCALE_POST) != 0;
     const bool nvls_exact = (post || is_pow2_scale(scale)) && (wire_dtype != TOK_F16 || post);
-    if (!forced && algo == TOK_ALGO_TWO_SHOT && c->mc_va && c->world >= 3) algo = TOK_ALGO_NVLS;
+    // (pick_algo's rule stands for pool buckets too: with 3-4 replicas the in-switch reduction stops
+    // paying off past ~12 MiB — measured in place at N=4 on the 22.9 / 28.3 MB DDP buckets: P2P
+    // reduce+push 83.0 us vs NVLS 95.7 us, profiles/r02_zc_tune_n4.json; with >= 5 replicas NVLS wins:
+    // 81 vs 98 us at N=8, profiles/r02_zc_tune_n8.json)
     if (algo == TOK_ALGO_NVLS && !nvls_exact) {
       if (forced)
         inplace = false;  // honour the forced algorithm through the staged kernel
