@@ -152,7 +152,8 @@ def test_golden_gloo_vectors(tok_lib, n_gpus):
                     x = torch.from_numpy(g["randn_x32_r%d" % r].copy()).to("cuda:%d" % devs[r])
                     xb = harness.to_torch(g["randn_xb_r%d" % r], "bf16", "cuda:%d" % devs[r])
                     comm.allreduce_bucket(x, x, scale=1.0 / world, stream=st)
-                    comm.allreduce_bucket(xb, xb, scale=1.0 / world, stream=st)
+                    st.synchronize()   # threads share one CUDA context: nothing queued behind a
+                    comm.allreduce_bucket(xb, xb, scale=1.0 / world, stream=st)   # waiting kernel
                     st.synchronize()
                 comm.status()
                 outs[r] = (x.cpu().numpy(), harness.from_torch(xb, "bf16"))
@@ -448,7 +449,7 @@ def test_elastic_reform_in_place(tok_lib, n_gpus):
         c.close()
 
 
-def test_elastic_training_without_torch_distributed(tok_lib, n_gpus):
+def test_elastic_training_without_torch_distributed(tok_lib, n_gpus, monkeypatch):
     """BASELINE config 2 in miniature (rescale 2 -> 4 -> 2 mid-run): ElasticDataParallel keeps its
     gradient buckets in the symmetric pool, averages them with the zero-copy kernel, and survives
     peer-group re-forms without restarting any process.  Every averaged bucket is checked bit-for-bit
@@ -467,7 +468,23 @@ def test_elastic_training_without_torch_distributed(tok_lib, n_gpus):
     # never dispatched, and both time out (tools/thread_arrival_diag.py).  One context per replica —
     # processes, the product shape — is what tests/test_controller_gpu.py runs the zero-copy + re-form
     # combination in; this test keeps the pool buckets but exchanges them with the staged kernels.
-    os.environ["TOK_DISABLE_ZERO_COPY"] = "1"
+    monkeypatch.setenv("TOK_DISABLE_ZERO_COPY", "1")
+    # For the same reason nothing at all may be queued behind a kernel that waits for a peer's kernel
+    # (a hand-over is several collectives with copies in between): in this test every collective is
+    # followed by a synchronize of the stream it was launched on.
+    real_bcast, real_ar = Communicator.broadcast, Communicator.allreduce_bucket
+
+    def bcast_sync(self, buf, root=0, stream=None):
+        out = real_bcast(self, buf, root, stream=stream)
+        (stream or torch.cuda.current_stream(buf.device)).synchronize()
+        return out
+
+    def ar_sync(self, inp, out=None, **kw):
+        res = real_ar(self, inp, out, **kw)
+        (kw.get("stream") or torch.cuda.current_stream(inp.device)).synchronize()
+        return res
+    monkeypatch.setattr(Communicator, "broadcast", bcast_sync)
+    monkeypatch.setattr(Communicator, "allreduce_bucket", ar_sync)
     path = os.path.join(tempfile.mkdtemp(prefix="tok8s-edp-"), "r")
     devs = list(range(4)) if n_gpus >= 4 else [0] * 4
     state, errs = {}, []
@@ -559,6 +576,5 @@ def test_elastic_training_without_torch_distributed(tok_lib, n_gpus):
     run_all(lambda i: state[i]["edp"].reform(2, keep.index(i), 0b0101, 2), keep)
     step(keep, "w2c")
     assert state[0]["comm"].caps().epoch == 2
-    os.environ.pop("TOK_DISABLE_ZERO_COPY", None)
     for s in state.values():
         s["comm"].close()
