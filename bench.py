@@ -414,7 +414,11 @@ def run_ours(args):
                 "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu "
                                   "--set full at these bucket sizes (profiles/traffic.json)",
                 "note": "world=1 degenerates to the fused scale/cast: bytes = S_in + S_out; one "
-                        "launch between two CUDA events, launch latency included"}
+                        "launch between two CUDA events, launch latency included.  traffic is about "
+                        "S_in alone: the in-place result stays in the 126 MB L2 (written back after "
+                        "the kernel), and the kernel is latency-bound at this size (ncu: DRAM at "
+                        "~30 % of peak for ~10 us) — ATen's own mul_ takes the same 12.3 us "
+                        "back to back on the 28 MB bucket (profiles/r02_local_bench_n1.json)"}
     else:
         algbw = wire_bytes / (ar_ms_max * 1e-3) / 1e9 if ar_ms_max > 0 else 0.0
         busbw = algbw * 2.0 * (world - 1) / world
