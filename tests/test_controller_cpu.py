@@ -316,3 +316,29 @@ def test_metrics_endpoint_and_replica_telemetry(tok_lib, tmp_path):
     assert 'torch_on_k8s_allreduce_busbw_gbps{job="j"} 512.5' in text
     assert 'torch_on_k8s_reform_latency_seconds_count{job="j"} 1.0' in text
     assert "torch_on_k8s_jobs_created_total" in text and "torch_on_k8s_tenant_queue_jobs_pending_count" in text
+
+
+def test_joiner_waits_for_the_membership_that_lists_it(tmp_path):
+    """A replica started into a running job joins at the epoch the controller ANNOUNCES (not the one
+    it was started at): it waits for the first document with epoch >= its own that lists it; a
+    membership that never lists it (a reverted scale-out) times out instead of joining a wrong group."""
+    import threading
+    import time
+    from torch_on_k8s_b200.worker import membership_update, wait_for_membership
+    rdzv = str(tmp_path / "tok8s-j-1")
+
+    def publish(doc, delay):
+        time.sleep(delay)
+        with open(rdzv + ".members.tmp", "w") as f:
+            json.dump(doc, f)
+        os.replace(rdzv + ".members.tmp", rdzv + ".members")
+    with open(rdzv + ".members", "w") as f:     # an older membership without the joiner
+        json.dump({"epoch": 1, "world": 2, "ranks": {"j-master-0": 0, "j-worker-0": 1}}, f)
+    doc3 = {"epoch": 3, "world": 3, "survivor_mask": 3,
+            "ranks": {"j-master-0": 0, "j-worker-0": 1, "j-worker-1": 2}}
+    threading.Thread(target=publish, args=(doc3, 0.3), daemon=True).start()
+    assert wait_for_membership(rdzv, "j-worker-1", 2, timeout_s=10) == (2, 3, 3)
+    with pytest.raises(TimeoutError):
+        wait_for_membership(rdzv, "j-worker-9", 2, timeout_s=0.3)
+    assert membership_update(doc3, "j-worker-0", 1) == (3, 1, 3, 3)     # survivor's step
+    assert membership_update(doc3, "j-worker-0", 3) is None             # already at that epoch

@@ -538,3 +538,28 @@ def test_dag_ready_with_zero_task_upstream_and_missing_phases(tok_lib):
     for phases in ({}, {"Master": "Running"}, {"master": [None]}, {"Master": [1, 2]}):
         job.dag_ready("Master", phases)
         job.dag_ready("Worker", phases)       # no crash on malformed values either
+
+
+def test_torchjob_scale_keeps_status_and_caps_min_members(tok_lib):
+    """Row a7 trigger: a spec update of numTasks on a live job object (TorchJob.scale) keeps status /
+    conditions and every other field, and MinMember never exceeds NumTasks (volcano.go:134-137)."""
+    c = {"name": "torch", "image": "i", "command": ["x"]}
+    m = {"metadata": {"name": "s", "namespace": "default"},
+         "spec": {"minMembers": {"Master": 1, "Worker": 7},
+                  "torchTaskSpecs": {"Master": {"template": {"spec": {"containers": [c]}}},
+                                     "Worker": {"numTasks": 7, "template": {"spec": {"containers": [c]}}}}}}
+    job = TorchJob(m)
+    job.set_condition("Created", "JobCreated", "created", "2026-01-01T00:00:00Z")
+    assert job.world_size == 8 and job.cluster_spec("worker", 6)["rank"] == 7
+    job.scale("Worker", 3)
+    d = job.to_dict()
+    assert job.world_size == 4 and d["spec"]["minMembers"] == {"Master": 1, "Worker": 3}
+    assert job.last_condition() == "Created"                       # status survived the edit
+    assert job.cluster_spec("worker", 2)["env"][4] == {"name": "WORLD_SIZE", "value": "4"}
+    assert job.gang_admit(4)["admitted"] and not job.gang_admit(3)["admitted"]
+    job.scale("Worker", 7)
+    assert job.world_size == 8 and job.to_dict()["spec"]["minMembers"]["Worker"] == 3   # never raised
+    with pytest.raises(KeyError):
+        job.scale("Chief", 1)
+    with pytest.raises(ValueError):
+        job.scale("Worker", -1)
