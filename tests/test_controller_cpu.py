@@ -342,3 +342,64 @@ def test_joiner_waits_for_the_membership_that_lists_it(tmp_path):
         wait_for_membership(rdzv, "j-worker-9", 2, timeout_s=0.3)
     assert membership_update(doc3, "j-worker-0", 1) == (3, 1, 3, 3)     # survivor's step
     assert membership_update(doc3, "j-worker-0", 3) is None             # already at that epoch
+
+
+def test_scale_in_drains_replicas_gracefully(tok_lib, tmp_path, monkeypatch):
+    """In-place scale-in: the replicas that fall out of [0, numTasks) are NOT killed on the spot (their
+    peers would find them dead in the middle of a gradient exchange): they are dropped from the
+    published membership first, leave on their own at a step boundary, and only then does the
+    controller reap them and free their GPU slots; one that overstays drain_grace_s is deleted the
+    reference's way (reconcileOnePod, pod.go:648-651)."""
+    import time
+    monkeypatch.setenv("RUN_S", "30")
+    monkeypatch.setenv("EXIT_WHEN_DROPPED", "1")
+    m = manifest("dr", free_port(), workers=2)
+    for tt in ("Master", "Worker"):
+        m["spec"]["torchTaskSpecs"][tt]["template"]["spec"]["containers"][0]["command"] = \
+            [sys.executable, os.path.join(HERE, "cpu_elastic_replica.py")]
+    ctl = Controller(num_gpus=3, rdzv_dir=str(tmp_path), log_dir=str(tmp_path / "logs"),
+                     drain_grace_s=20)
+    uid = ctl.submit(m)
+    t0 = time.time()
+    while time.time() - t0 < 20 and ctl.jobs[uid].job.last_condition() != "Running":
+        ctl.tick()
+        time.sleep(0.05)
+    assert len(ctl.free_gpus) == 0
+    assert ctl.scale(uid, "Worker", 1) == 1
+    t1 = time.time()
+    while time.time() - t1 < 15 and not any(e[2] == "SuccessfulDeletePod" for e in ctl.events):
+        ctl.tick()
+        time.sleep(0.05)
+    took = time.time() - t1
+    order = [e[2] for e in ctl.events if e[2] in ("DrainingPod", "MembershipPublished", "SuccessfulDeletePod")]
+    assert order == ["DrainingPod", "MembershipPublished", "SuccessfulDeletePod"]
+    assert took < 10                                    # it left by itself, long before the grace period
+    doc = [json.loads(e[3]) for e in ctl.events if e[2] == "MembershipPublished"][-1]
+    assert doc == {"epoch": 1, "world": 2, "survivor_mask": 0b011,
+                   "ranks": {"dr-master-0": 0, "dr-worker-0": 1}}
+    assert len(ctl.free_gpus) == 1 and "Worker" in ctl.jobs[uid].replicas and \
+        sorted(ctl.jobs[uid].replicas["Worker"]) == [0]
+    # a replica that does not leave is deleted when the grace period is over
+    monkeypatch.delenv("EXIT_WHEN_DROPPED")
+    ctl2 = Controller(num_gpus=3, rdzv_dir=str(tmp_path / "b"), drain_grace_s=1.0)
+    os.makedirs(tmp_path / "b", exist_ok=True)
+    m2 = manifest("dr2", free_port(), workers=2)
+    for tt in ("Master", "Worker"):
+        m2["spec"]["torchTaskSpecs"][tt]["template"]["spec"]["containers"][0]["command"] = \
+            [sys.executable, os.path.join(HERE, "cpu_elastic_replica.py")]
+    uid2 = ctl2.submit(m2)
+    t0 = time.time()
+    while time.time() - t0 < 20 and ctl2.jobs[uid2].job.last_condition() != "Running":
+        ctl2.tick()
+        time.sleep(0.05)
+    ctl2.scale(uid2, "Worker", 1)
+    t1 = time.time()
+    while time.time() - t1 < 15 and not any(e[2] == "SuccessfulDeletePod" for e in ctl2.events):
+        ctl2.tick()
+        time.sleep(0.05)
+    assert 0.9 <= time.time() - t1 < 10 and len(ctl2.free_gpus) == 1
+    for c in (ctl, ctl2):
+        for mj in c.jobs.values():
+            for reps in mj.replicas.values():
+                for r in reps.values():
+                    c._kill(r)
