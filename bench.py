@@ -530,6 +530,13 @@ def run_ours(args):
         "roofline": roof,
         "roofline_isolated": iso,
     }
+    if world == 1:
+        line["world1_note"] = ("at world 1 the per-bucket exchange is the fused scale/cast with scale "
+                               "1 on an in-place bucket: an identity libtok8s elides by default (no "
+                               "launch, no HBM pass).  This run passes TOK_FLAG_NO_ELIDE so that the "
+                               "hot-path kernel runs and is measured in-step (gpu_launches counts "
+                               "those launches), as the reference's own hook does (div_(1) + "
+                               "allreduce)")
     if nccl is not None:
         line["nccl"] = nccl
         line["vs_nccl"] = {"step": value / nccl["value"], "e2e": e2e_value / nccl["e2e"]["value"],
