@@ -106,7 +106,13 @@ def main():
                     if algo == 0:
                         row["auto_algo"] = _ffi.ALGO_NAMES[comm.algo_for(nbytes)]
                 # zero-copy: the same exchange on buckets that live in the symmetric pool
-                if args.zero_copy and world > 1 and nbytes >= (1 << 16):
+                # the pool must hold this size's buffer set plus the check buffer on top of what the
+                # torch MemPool already caches from the smaller sizes (it does not give segments back)
+                pool_ok = (nbuf + 1) * nbytes <= comm.symm_info()[1] - comm.symm_info()[2]
+                if args.zero_copy and world > 1 and nbytes >= (1 << 16) and not pool_ok:
+                    row["zc_skipped"] = "symmetric pool too small for %d x %d bytes (TOK_SYMM_POOL_MB)" % \
+                        (nbuf + 1, nbytes)
+                if args.zero_copy and world > 1 and nbytes >= (1 << 16) and pool_ok:
                     zbufs = [comm.symm_empty(count, dt).fill_(float(rank + 1)) for _ in range(nbuf)]
                     zalgos = [(0, "zc_auto"), (3, "zc_two_shot")]
                     if caps.multicast:
@@ -155,6 +161,11 @@ def main():
                 if rank == 0:
                     print(json.dumps({k: (round(v, 2) if isinstance(v, float) else v)
                                       for k, v in row.items()}), flush=True)
+                    # written after every row: a run that dies at the largest sizes keeps its rows
+                    os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
+                    with open("%s_n%d.json" % (args.out, world), "w") as f:
+                        json.dump(dict(world=world, when=time.time(), partial=True,
+                                       gpu=torch.cuda.get_device_name(0), rows=results), f, indent=1)
                 del bufs, b
                 nbytes *= 4 if nbytes < (1 << 20) else 2
         comm.close()
